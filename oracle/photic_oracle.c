@@ -22,6 +22,22 @@
 #include "../include/photic_spectra.h"
 
 #define PHO_PI 3.141592653589793 /* common.h:19 */
+
+/* what-if PHO_VARIANT_LIBM_JITTER: a pure function of the argument bits nudges the result of
+ * exp/log/pow by -1/0/+1 ulp, emulating "another correctly-working libm" (e.g. CUDA's). */
+static int g_jitter = 0;
+static double jit(double y, double x) {
+  union { double d; unsigned long long u; } a, b;
+  unsigned long long h;
+  if (!g_jitter) return y;
+  a.d = x; b.d = y;
+  h = a.u * 0x9E3779B97F4A7C15ULL; h ^= h >> 29; h *= 0xBF58476D1CE4E5B9ULL; h ^= h >> 32;
+  switch (h % 4) { case 0: b.u += 1; break; case 1: b.u -= 1; break; default: break; }
+  return b.d;
+}
+#define exp(x) jit(exp(x), (x))
+#define log(x) jit(log(x), (x))
+#define pow(x, y) jit(pow((x), (y)), (x) * 1.37 + (y))
 #define PHO_BIG 1.0e10           /* common.h:21 */
 
 /* ------------------------------------------------------------------------------------------
@@ -692,6 +708,7 @@ int pho_invert_pixels_variant(int variant, int nscenes, int maxb, const int *n_b
       (2 * n_spatial - 1) * (2 * n_spatial - 1) > PHO_MAX_REGIONS)
     return 1;
   model_init(&m, nscenes, maxb, n_bands, wavelengths, theta_v, theta_w, h_tide, n_smooth, n_spatial, n_bottoms);
+  g_jitter = (variant & PHO_VARIANT_LIBM_JITTER) != 0; /* after model_init: tables stay exact */
 #if _OPENMP
   if (nthreads > 0) omp_set_num_threads(nthreads);
 #pragma omp parallel

@@ -31,6 +31,7 @@ extern "C" {
 #define PHO_VARIANT_EXACT 0
 #define PHO_VARIANT_TREE_SUM 1      /* error sum: 32 strided partials + butterfly tree     */
 #define PHO_VARIANT_INCR_CENTROID 2 /* centroid from a running vertex sum, resummed at checks */
+#define PHO_VARIANT_LIBM_JITTER 4   /* exp/log/pow results nudged by a deterministic -1/0/+1 ulp */
 
 int pho_record_len(int nscenes, int maxb);
 
