@@ -1,0 +1,168 @@
+/*
+ * photic_b200.h -- C ABI of libphotic_b200.so: the B200 (sm_100a, FP64) replacement for the
+ * per-pixel semi-analytical inversion of stblake/photic.
+ *
+ * Drop-in boundary. The reference's entry point for this path is
+ *
+ *     void samodel(scene scene_data[], geogrid gridded_data[], int *scene_indexes, int nscenes,
+ *                  bool empirical_depth_present, geogrid empirical_depths,
+ *                  int n_smoothing_radius, int n_spatial, int n_bottoms,
+ *                  float **depth, ... float **index_optical_depth, ...);      model/samodel.h:8-19
+ *
+ * called once from model/bam.c:3236-3241. photic_b200/host/samodel_b200.c keeps that exact symbol
+ * and signature (it replaces model/samodel.c in the reference's link line) and forwards to the
+ * functions below. Everything here is extern "C", plain pointers and sizes, no torch/C++ types.
+ * All functions return 0 on success or a PHB_E* code; phb_error_string() describes it (the
+ * reference itself has no error channel: it printf()s and exit(1)s, model/common.h:62-67 -- the
+ * shim reproduces that).
+ *
+ * There is NO CPU fallback: every compute entry point fails with PHB_ENODEVICE when no CUDA
+ * device is usable.
+ */
+#ifndef PHOTIC_B200_H_
+#define PHOTIC_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PHB_MAX_SCENES 16  /* acquisition dates per inversion           */
+#define PHB_MAX_BANDS 8    /* spectral bands per scene                  */
+#define PHB_MAX_BOTTOMS 8  /* substrate classes (table of samodel.c:464) */
+#define PHB_MAX_SPATIAL 3  /* NSPATIAL: regions = (2*NSPATIAL-1)^2 <= 25 */
+
+enum {
+  PHB_OK = 0,
+  PHB_EINVAL = 1,    /* bad descriptor / argument                         */
+  PHB_ENODEVICE = 2, /* no usable CUDA device (there is no CPU fallback)   */
+  PHB_ECUDA = 3,     /* a CUDA call failed; see phb_error_string           */
+  PHB_ENOMEM = 4     /* host or device allocation failed                   */
+};
+
+/*
+ * What SCENE ... / SET NSMOOTH|NSPATIAL|NBOTTOMS leave in the reference's globals
+ * (scene: model/common.h:194-218; defaults model/common.c:152), flattened to a POD.
+ * Only the fields samodel() reads are present.
+ */
+typedef struct phb_scene_desc {
+  int32_t n_scenes;
+  int32_t n_bands[PHB_MAX_SCENES];
+  int32_t wavelengths[PHB_MAX_SCENES][PHB_MAX_BANDS]; /* integer nm: scene.wavelengths is int[] */
+  double theta_view[PHB_MAX_SCENES];                  /* degrees, scene.theta_v */
+  double theta_sun[PHB_MAX_SCENES];                   /* degrees, scene.theta_w */
+  double h_tide[PHB_MAX_SCENES];                      /* metres,  scene.H_tide  */
+  int32_t n_smoothing_radius;                         /* SET NSMOOTH  (default 1) */
+  int32_t n_spatial;                                  /* SET NSPATIAL (default 2) */
+  int32_t n_bottoms;                                  /* SET NBOTTOMS (default 3) */
+  int32_t nrows, ncols;                               /* raster held by THIS call (shard incl. halo rows) */
+  float nodata;                                       /* geogrid.nodata_value of the reflectance grids */
+  int32_t prior_present;                              /* MODEL ... DEPTHS grid given (bam.c:3077)   */
+  float prior_nodata;
+} phb_scene_desc;
+
+/*
+ * Output planes, each [nrows][ncols] float32 unless noted; any pointer may be NULL (not wanted).
+ * Cell values follow samodel(): defaults of samodel.c:819-829 where nothing is inverted, depth
+ * NEGATED (samodel.c:1486-1490), model_error holds the Rrs error (samodel.c:1121).
+ * Rows outside [row_begin,row_end) are left untouched.
+ */
+typedef struct phb_outputs {
+  float *depth, *model_error, *bottom_albedo, *bottom_sand, *bottom_seagrass, *bottom_coral;
+  float *K_min, *bottom_type, *index_optical_depth;
+  float *K;          /* [n_scenes][max_bands][nrows][ncols]  (<scene>_K_<band>.nc, samodel.c:1513-1560) */
+  float *P, *G, *X;  /* [n_scenes][nrows][ncols]             (<scene>_{P,G,X}.nc, samodel.c:1562-1596) */
+  uint8_t *converged; /* md->converged  (samodel.c:2398-2402)                                   */
+  int32_t *n_evals;   /* md->n_iterations = nelmin icount (samodel.c:2396)                      */
+} phb_outputs;
+
+/* Counters of one inversion call (for throughput / roofline accounting). */
+typedef struct phb_stats {
+  int64_t n_valid;      /* pixels inverted                                               */
+  int64_t n_shallow;    /* of which with all NBOTTOMS substrates (h_prior <= 8 m)        */
+  int64_t n_evals;      /* objective evaluations, incl. the 2 outside nelmin per start   */
+  int64_t n_iters;      /* Nelder-Mead iterations                                        */
+  int64_t n_converged;  /* pixels with ifault == 0                                       */
+  double alg_flops;     /* sum_px evals*F_eval(Nr,Ns,Nb) + iters*(n^2+9n): the reference's literal op count */
+  float ms_classify, ms_solve; /* CUDA-event times of the two kernels on the launch stream */
+  float ms_h2d, ms_d2h;        /* host entry point only                                      */
+  int32_t warps_per_cta, ctas, smem_bytes, regs; /* launch geometry actually used          */
+} phb_stats;
+
+typedef struct phb_ctx phb_ctx; /* one per device; owns scratch, queues, simplex slabs */
+
+int phb_version(void);
+const char *phb_error_string(int code);
+int phb_device_count(void);
+
+int phb_ctx_create(int device, phb_ctx **out);
+void phb_ctx_destroy(phb_ctx *ctx);
+
+/*
+ * Scene-level constants samodel() derives once (samodel.c:505-618): a0, a1, a_w, b_bw and the
+ * bottom spectra interpolated at each band, secants, a_w(640). Host-only, no device needed.
+ * out layout: [n_scenes][PHB_MAX_BANDS][4 + PHB_MAX_BOTTOMS] then a_w640, sec_view[], sec_sun[].
+ */
+int phb_band_tables(const phb_scene_desc *desc, double *out_tables, double *out_aux);
+
+/*
+ * Inversion of rows [row_begin,row_end) of the raster, inputs and outputs in DEVICE memory.
+ *   d_planes : [sum_s n_bands[s]][nrows][ncols] float32, scene-major then band
+ *   d_prior  : [nrows][ncols] float32 DEPTHS grid (negative-down) or NULL
+ *   d_debug  : optional [n_valid_capacity][phb_debug_record_len()] doubles + int32 pixel index
+ *              per record, full-precision per-pixel results for parity tests; NULL in production
+ * Edge clamping of the (2*n_spatial-1)^2 neighbourhood happens at the raster's own edges
+ * (samodel.c:2971-2989): give a shard its halo rows and the result equals the unsharded one.
+ * Asynchronous on `stream` (a cudaStream_t) except for the final stats read-back.
+ */
+int phb_invert_device(phb_ctx *ctx, const phb_scene_desc *desc, const float *d_planes, const float *d_prior,
+                      int row_begin, int row_end, const phb_outputs *d_out, void *stream, phb_stats *stats);
+
+/* Same with HOST buffers: copies in, inverts, copies out (what the samodel() shim calls). */
+int phb_invert_host(phb_ctx *ctx, const phb_scene_desc *desc, const float *const *h_planes, const float *h_prior,
+                    int row_begin, int row_end, const phb_outputs *h_out, phb_stats *stats);
+
+/* Parity-test hook: like phb_invert_host but also returns the full-precision per-pixel record
+ * (layout of oracle/ref_harness.c: 16 + n_scenes*max_bands + 3*n_scenes doubles) for every
+ * inverted pixel. rec: [capacity][reclen]; pix: [capacity] linear index i*ncols+j. */
+int phb_debug_record_len(const phb_scene_desc *desc);
+int phb_invert_host_debug(phb_ctx *ctx, const phb_scene_desc *desc, const float *const *h_planes,
+                          const float *h_prior, int row_begin, int row_end, const phb_outputs *h_out,
+                          double *rec, int32_t *pix, int32_t *n_iters, int64_t capacity, phb_stats *stats);
+
+/* Known-answer hooks (device evaluation of the forward model / objective on caller-supplied
+ * parameter vectors, mirroring oracle/ref_harness.c:ref_error_kat) and of the exact libm port. */
+int phb_kat_objective(phb_ctx *ctx, const phb_scene_desc *desc, int n_bottoms_active, int n_regions, int origin,
+                      const double *rrs_measured, int nparams, int nvec, const double *params, double *out6);
+int phb_kat_math(phb_ctx *ctx, int fn /*0 exp,1 log,2 pow*/, const double *x, const double *y, int64_t n, double *out);
+
+/*
+ * REFINE (model/refine.c:12-302): point-wise depth remap.
+ * args: [0] clip_min [1] clip_max [2] scale_min [3] scale_max [4] shape [5] linear_m [6] linear_c
+ *       [7] scrap_min [8] scrap_max [9] power_a [10] power_b
+ * Without PHB_REFINE_CLIP the grid's own min/max (nodata skipped) are used (refine.c:215-225);
+ * minmax_io (2 floats, nullable) lets a sharded caller all-reduce them: in = local, out = used.
+ */
+#define PHB_REFINE_CLIP 1
+#define PHB_REFINE_SCALE 2
+#define PHB_REFINE_LINEAR 4
+#define PHB_REFINE_SCRAP 8
+#define PHB_REFINE_POWER 16
+int phb_refine_minmax_device(phb_ctx *ctx, const float *d_in, int64_t n, float nodata, float *h_minmax, void *stream);
+int phb_refine_device(phb_ctx *ctx, const float *d_in, float nodata, const float *d_land, float land_nodata,
+                      const float *d_shallow, float shallow_nodata, int64_t n, int flags, const float *args,
+                      const float *minmax, float *d_out, void *stream);
+int phb_refine_host(phb_ctx *ctx, const float *h_in, float nodata, const float *h_land, float land_nodata,
+                    const float *h_shallow, float shallow_nodata, int nrows, int ncols, int flags, const float *args,
+                    float *h_out);
+
+/* FP64 pipe peak of this device, measured with a dependent-free DFMA chain kernel (MEASURED_PEAKS.json
+ * has no FP64 entry). Returns TFLOP/s (2 flops per DFMA) and the kernel time. */
+int phb_fp64_peak(phb_ctx *ctx, double *tflops, float *ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PHOTIC_B200_H_ */

@@ -1,0 +1,50 @@
+"""Builds the product library in-tree: photic_b200/csrc/libphotic_b200.so (sm_100a only).
+
+    python -m photic_b200.build            # or __graft_entry__.build()
+
+-fmad=false is part of the correctness contract (bit parity with the reference's non-FMA x86-64
+build; the FMAs that ARE wanted -- inside the glibc exp/log/pow port -- are explicit __fma_rn).
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(CSRC, "libphotic_b200.so")
+HOST_SHIM = os.path.join(HERE, "host", "libsamodel_b200.so")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-fmad=false",
+    "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v",
+]
+
+
+def _stale(target: str, sources: list[str]) -> bool:
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(s) > t for s in sources)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))]
+    srcs += [os.path.join(HERE, "..", "include", f) for f in ("photic_b200.h", "photic_spectra.h")]
+    if force or _stale(LIB, srcs):
+        nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+        cmd = [nvcc, *NVCC_FLAGS, "-o", LIB, os.path.join(CSRC, "photic_b200.cu")]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        log = r.stdout + r.stderr
+        with open(os.path.join(CSRC, "build.log"), "w") as f:
+            f.write(" ".join(cmd) + "\n" + log)
+        if verbose or r.returncode:
+            print(log, file=sys.stderr)
+        if r.returncode:
+            raise RuntimeError("nvcc failed; see photic_b200/csrc/build.log")
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

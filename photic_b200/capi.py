@@ -1,0 +1,146 @@
+"""ctypes binding of the C ABI in include/photic_b200.h (libphotic_b200.so).
+
+This is what a host application binds; nothing here computes. If the shared library is missing the
+import of :func:`lib` raises -- there is no Python or CPU fallback for the inversion.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "csrc", "libphotic_b200.so")
+
+MAX_SCENES, MAX_BANDS, MAX_BOTTOMS = 16, 8, 8
+
+_fp = C.POINTER(C.c_float)
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+_u8p = C.POINTER(C.c_uint8)
+
+
+class SceneDesc(C.Structure):
+    _fields_ = [
+        ("n_scenes", C.c_int32),
+        ("n_bands", C.c_int32 * MAX_SCENES),
+        ("wavelengths", (C.c_int32 * MAX_BANDS) * MAX_SCENES),
+        ("theta_view", C.c_double * MAX_SCENES),
+        ("theta_sun", C.c_double * MAX_SCENES),
+        ("h_tide", C.c_double * MAX_SCENES),
+        ("n_smoothing_radius", C.c_int32),
+        ("n_spatial", C.c_int32),
+        ("n_bottoms", C.c_int32),
+        ("nrows", C.c_int32),
+        ("ncols", C.c_int32),
+        ("nodata", C.c_float),
+        ("prior_present", C.c_int32),
+        ("prior_nodata", C.c_float),
+    ]
+
+
+class Outputs(C.Structure):
+    _fields_ = [(n, _fp) for n in ("depth", "model_error", "bottom_albedo", "bottom_sand", "bottom_seagrass",
+                                   "bottom_coral", "K_min", "bottom_type", "index_optical_depth", "K", "P", "G", "X")]
+    _fields_ += [("converged", _u8p), ("n_evals", _ip)]
+
+
+class Stats(C.Structure):
+    _fields_ = [
+        ("n_valid", C.c_int64), ("n_shallow", C.c_int64), ("n_evals", C.c_int64), ("n_iters", C.c_int64),
+        ("n_converged", C.c_int64), ("alg_flops", C.c_double), ("ms_classify", C.c_float), ("ms_solve", C.c_float),
+        ("ms_h2d", C.c_float), ("ms_d2h", C.c_float), ("warps_per_cta", C.c_int32), ("ctas", C.c_int32),
+        ("smem_bytes", C.c_int32), ("regs", C.c_int32),
+    ]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+SCALAR_PLANES = ("depth", "model_error", "bottom_albedo", "bottom_sand", "bottom_seagrass", "bottom_coral", "K_min",
+                 "bottom_type", "index_optical_depth")
+
+_lib = None
+
+
+class PhoticError(RuntimeError):
+    pass
+
+
+def lib() -> C.CDLL:
+    """Loads libphotic_b200.so (built by photic_b200.build). Raises if it is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise PhoticError(f"{LIB_PATH} not built: run `python -m photic_b200.build` (needs nvcc). "
+                              "photic_b200 has no CPU fallback.")
+        L = C.CDLL(LIB_PATH)
+        L.phb_error_string.restype = C.c_char_p
+        L.phb_error_string.argtypes = [C.c_int]
+        L.phb_ctx_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+        L.phb_ctx_destroy.argtypes = [C.c_void_p]
+        L.phb_ctx_destroy.restype = None
+        L.phb_band_tables.argtypes = [C.POINTER(SceneDesc), _dp, _dp]
+        L.phb_invert_device.argtypes = [C.c_void_p, C.POINTER(SceneDesc), C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                        C.POINTER(Outputs), C.c_void_p, C.POINTER(Stats)]
+        L.phb_invert_host.argtypes = [C.c_void_p, C.POINTER(SceneDesc), C.POINTER(C.c_void_p), C.c_void_p, C.c_int,
+                                      C.c_int, C.POINTER(Outputs), C.POINTER(Stats)]
+        L.phb_debug_record_len.argtypes = [C.POINTER(SceneDesc)]
+        L.phb_invert_host_debug.argtypes = [C.c_void_p, C.POINTER(SceneDesc), C.POINTER(C.c_void_p), C.c_void_p,
+                                            C.c_int, C.c_int, C.POINTER(Outputs), _dp, _ip, _ip, C.c_int64,
+                                            C.POINTER(Stats)]
+        L.phb_kat_objective.argtypes = [C.c_void_p, C.POINTER(SceneDesc), C.c_int, C.c_int, C.c_int, _dp, C.c_int,
+                                        C.c_int, _dp, _dp]
+        L.phb_kat_math.argtypes = [C.c_void_p, C.c_int, _dp, _dp, C.c_int64, _dp]
+        L.phb_refine_minmax_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_float, _fp, C.c_void_p]
+        L.phb_refine_device.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_float, C.c_void_p,
+                                        C.c_float, C.c_int64, C.c_int, _fp, _fp, C.c_void_p, C.c_void_p]
+        L.phb_refine_host.argtypes = [C.c_void_p, _fp, C.c_float, _fp, C.c_float, _fp, C.c_float, C.c_int, C.c_int,
+                                      C.c_int, _fp, _fp]
+        L.phb_fp64_peak.argtypes = [C.c_void_p, _dp, _fp]
+        _lib = L
+    return _lib
+
+
+EXPORTS = ["phb_version", "phb_error_string", "phb_device_count", "phb_ctx_create", "phb_ctx_destroy",
+           "phb_band_tables", "phb_invert_device", "phb_invert_host", "phb_debug_record_len", "phb_invert_host_debug",
+           "phb_kat_objective", "phb_kat_math", "phb_refine_minmax_device", "phb_refine_device", "phb_refine_host",
+           "phb_fp64_peak"]
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise PhoticError(f"photic_b200 error {rc}: {lib().phb_error_string(rc).decode()}")
+
+
+def make_desc(wavelengths, theta_view, theta_sun, h_tide, nrows, ncols, nodata=-9999.0, prior_present=True,
+              prior_nodata=-9999.0, n_smooth=1, n_spatial=2, n_bottoms=3) -> SceneDesc:
+    wl = np.asarray(wavelengths, dtype=np.int32)
+    ns = len(theta_sun)
+    if wl.ndim == 1:
+        wl = np.tile(wl, (ns, 1))
+    d = SceneDesc()
+    d.n_scenes = ns
+    tv = np.broadcast_to(np.asarray(theta_view, dtype=np.float64), (ns,))
+    for s in range(ns):
+        d.n_bands[s] = wl.shape[1]
+        for b in range(wl.shape[1]):
+            d.wavelengths[s][b] = int(wl[s, b])
+        d.theta_view[s] = float(tv[s])
+        d.theta_sun[s] = float(theta_sun[s])
+        d.h_tide[s] = float(h_tide[s])
+    d.n_smoothing_radius, d.n_spatial, d.n_bottoms = n_smooth, n_spatial, n_bottoms
+    d.nrows, d.ncols = nrows, ncols
+    d.nodata = nodata
+    d.prior_present = 1 if prior_present else 0
+    d.prior_nodata = prior_nodata
+    return d
+
+
+def desc_from_spec(spec, nrows=None, prior_present=True) -> SceneDesc:
+    ns = spec.n_dates
+    return make_desc(spec.wavelengths, spec.theta_view, [spec.theta_sun(s) for s in range(ns)],
+                     [spec.h_tide(s) for s in range(ns)], spec.nrows if nrows is None else nrows, spec.ncols,
+                     prior_present=prior_present, n_smooth=spec.n_smoothing_radius, n_spatial=spec.n_spatial,
+                     n_bottoms=spec.n_bottoms)

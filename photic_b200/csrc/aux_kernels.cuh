@@ -1,0 +1,194 @@
+/*
+ * aux_kernels.cuh -- known-answer kernels, REFINE (model/refine.c) and the FP64 peak probe.
+ */
+#ifndef PHOTIC_AUX_KERNELS_CUH_
+#define PHOTIC_AUX_KERNELS_CUH_
+
+#include "invert_kernel.cuh"
+
+namespace phb {
+
+/* ---- known answers: objective on caller-supplied parameter vectors (one warp) ------------------ */
+__global__ void kat_objective_kernel(const SolveParams p, int nb_active, int n_regions, int origin,
+                                     const double *meas, int nvec, const double *params, double *out6) {
+  const ModelConst &M = *p.M;
+  stage_cta(p, M, phb_smem);
+  __syncthreads();
+  Warp w;
+  bind_warp(w, p, phb_smem, 0, 0);
+  w.max_bands = M.max_bands;
+  w.Nr = n_regions; w.Nb = nb_active; w.origin = origin;
+  w.n = n_regions + 2 * n_regions * nb_active + 3 * w.Ns;
+  w.T = n_regions * w.SB;
+  for (int t = w.lane; t < w.T; t += 32) w.meas[t] = meas[t];
+  __syncwarp();
+  phm::Tables tb;
+  tb.exp_tab = reinterpret_cast<const uint64_t *>(w.exp_tab);
+  tb.log_tab = p.log_tab;
+  tb.pow_tab = p.pow_tab;
+  double Bs, Ps, Xs;
+  derive_pixel_constants(w, M, tb, Bs, Ps, Xs);
+  for (int v = 0; v < nvec; v++) {
+    for (int i = w.lane; i < w.n; i += 32) w.xmin[i] = params[(size_t)v * w.n + i];
+    __syncwarp();
+    const double e = objective(w, w.xmin, true);
+    if (w.lane == 0) {
+      double *o = out6 + (size_t)v * 6;
+      o[0] = e; o[1] = w.e_rrs; o[2] = w.e_depth; o[3] = w.e_bottom; o[4] = w.e_K; o[5] = w.bottom_albedo;
+    }
+    __syncwarp();
+  }
+}
+
+/* ---- known answers: the exact libm port --------------------------------------------------------- */
+__global__ void kat_math_kernel(int fn, const double *x, const double *y, long long n, double *out,
+                                const unsigned long long *exp_tab, const double *log_tab, const double *pow_tab) {
+  phm::Tables tb;
+  tb.exp_tab = reinterpret_cast<const uint64_t *>(exp_tab);
+  tb.log_tab = log_tab;
+  tb.pow_tab = pow_tab;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    double r;
+    if (fn == 0) r = phm::exp(x[i], tb.exp_tab);
+    else if (fn == 1) r = phm::log(x[i], tb.log_tab);
+    else r = phm::pow(x[i], y[i], tb);
+    out[i] = r;
+  }
+}
+
+/* ---- REFINE, model/refine.c:215-301 --------------------------------------------------------------
+ * Point-wise; every variable of the reference is a float, pow()/fabs() promote to double and the
+ * result is narrowed back. pow here is the exact host-libm port, so results equal the CPU's. */
+
+__host__ __device__ inline unsigned int float_to_ordered(float f) {
+  unsigned int u;
+#if defined(__CUDA_ARCH__)
+  u = __float_as_uint(f);
+#else
+  memcpy(&u, &f, 4);
+#endif
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__host__ __device__ inline float ordered_to_float(unsigned int o) {
+  unsigned int u = (o & 0x80000000u) ? (o & 0x7fffffffu) : ~o;
+#if defined(__CUDA_ARCH__)
+  return __uint_as_float(u);
+#else
+  float f; memcpy(&f, &u, 4); return f;
+#endif
+}
+
+/* array_min2 / array_max2, common.c:1224-1262 (nodata skipped with approx_equal 1e-4) */
+__global__ void refine_minmax_kernel(const float *in, long long n, float nodata, unsigned int *mm) {
+  unsigned int lo = 0xffffffffu, hi = 0u;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = __ldg(in + i);
+    if (approx_equal_f(v, nodata, 1.0e-4f)) continue;
+    if (v != v) continue; /* NaN never wins a < or > comparison */
+    const unsigned int o = float_to_ordered(v);
+    lo = o < lo ? o : lo;
+    hi = o > hi ? o : hi;
+  }
+  lo = __reduce_min_sync(kFull, lo);
+  hi = __reduce_max_sync(kFull, hi);
+  if ((threadIdx.x & 31) == 0) { atomicMin(mm + 0, lo); atomicMax(mm + 1, hi); }
+}
+
+struct RefineParams {
+  const float *in, *land, *shallow;
+  float *out;
+  long long n;
+  float nodata, land_nodata, shallow_nodata;
+  int flags;
+  float oldmin, oldmax, dmin, dmax, scale, linear_m, linear_c, scrapmin, scrapmax, power_a, power_b;
+  float sca, scb;
+  const unsigned long long *exp_tab; const double *log_tab; const double *pow_tab;
+};
+
+/* host part of refine.c:215-238: the rescale coefficients (uses the host libm pow, as the reference) */
+inline RefineParams make_refine_params(int flags, const float *args, const float *minmax) {
+  RefineParams r;
+  memset(&r, 0, sizeof(r));
+  r.flags = flags;
+  r.oldmin = args[0]; r.oldmax = args[1]; r.dmin = args[2]; r.dmax = args[3]; r.scale = args[4];
+  r.linear_m = args[5]; r.linear_c = args[6]; r.scrapmin = args[7]; r.scrapmax = args[8];
+  r.power_a = args[9]; r.power_b = args[10];
+  if (!(flags & PHB_REFINE_CLIP)) { r.oldmin = minmax[0]; r.oldmax = minmax[1]; }
+  if (flags & PHB_REFINE_SCALE) {
+    float smin = (float)pow(fabs((double)r.oldmin), (double)r.scale);
+    if (r.oldmin < 0.0) smin = (float)((double)smin * -1.0);
+    float smax = (float)pow(fabs((double)r.oldmax), (double)r.scale);
+    if (r.oldmax < 0.0) smax = (float)((double)smax * -1.0);
+    volatile float num = r.oldmax - r.oldmin, den = smax - smin;
+    r.sca = num / den;
+    volatile float t0 = r.oldmax * smin, t1 = r.oldmin * smax;
+    volatile float num2 = t0 - t1, den2 = smin - smax;
+    r.scb = num2 / den2;
+  }
+  return r;
+}
+
+__global__ void refine_kernel(const RefineParams p) {
+  phm::Tables tb;
+  tb.exp_tab = reinterpret_cast<const uint64_t *>(p.exp_tab);
+  tb.log_tab = p.log_tab;
+  tb.pow_tab = p.pow_tab;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < p.n; i += (long long)gridDim.x * blockDim.x) {
+    const bool open = (p.land == nullptr && p.shallow == nullptr) ||
+                      ((p.land != nullptr && p.land[i] != p.land_nodata) &&
+                       (p.shallow != nullptr && p.shallow[i] != p.shallow_nodata));
+    if (!open) { p.out[i] = p.nodata; continue; }
+    float depth = p.in[i];
+    if (depth == p.nodata) { p.out[i] = p.nodata; continue; }
+    if (p.flags & PHB_REFINE_CLIP) {
+      if (depth < p.oldmin) depth = p.oldmin;
+      else if (depth > p.oldmax) depth = p.oldmax;
+    }
+    if (p.flags & PHB_REFINE_LINEAR) depth = __fadd_rn(__fmul_rn(p.linear_m, depth), p.linear_c);
+    if (p.flags & PHB_REFINE_SCALE) {
+      if (p.scale != 1.0) {
+        float v = __fsub_rn(__fmul_rn(p.dmin, p.oldmax), __fmul_rn(p.dmax, p.oldmin));
+        v = __fadd_rn(v, __fmul_rn(p.dmax, depth));
+        v = __fsub_rn(v, __fmul_rn(p.dmin, depth));
+        v = __fdiv_rn(v, __fsub_rn(p.oldmax, p.oldmin));
+        depth = (float)__dadd_rn(__dmul_rn((double)p.sca, phm::pow(fabs((double)v), (double)p.scale, tb)), (double)p.scb);
+        if (v < 0.0) depth = (float)((double)depth * -1.0);
+      } else {
+        const float den = __fsub_rn(p.oldmax, p.oldmin);
+        const float alpha = __fdiv_rn(__fsub_rn(__fmul_rn(p.oldmax, p.dmin), __fmul_rn(p.oldmin, p.dmax)), den);
+        const float beta = __fdiv_rn(__fsub_rn(p.dmax, p.dmin), den);
+        depth = __fadd_rn(alpha, __fmul_rn(beta, depth));
+      }
+    }
+    if (p.flags & PHB_REFINE_SCRAP) {
+      if (depth < p.scrapmin || depth > p.scrapmax) { p.out[i] = p.nodata; continue; }
+    }
+    if (p.flags & PHB_REFINE_POWER) {
+      const double pw = phm::pow(fabs((double)depth), (double)p.power_b, tb);
+      if (depth < 0.0) depth = (float)__dmul_rn(__dmul_rn(-1.0, (double)p.power_a), pw);
+      else depth = (float)__dmul_rn((double)p.power_a, pw);
+    }
+    p.out[i] = depth;
+  }
+}
+
+/* ---- FP64 pipe peak: kPeakChains independent DFMA chains per thread ------------------------------ */
+constexpr int kPeakChains = 8;
+__global__ void dfma_peak_kernel(double *sink, int iters) {
+  double a[kPeakChains];
+  const double b = 1.0000001, c = 1.0e-9 * (threadIdx.x + 1);
+#pragma unroll
+  for (int k = 0; k < kPeakChains; k++) a[k] = 1.0 + 0.001 * k + 1e-6 * threadIdx.x;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int k = 0; k < kPeakChains; k++) a[k] = __fma_rn(a[k], b, c);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int k = 0; k < kPeakChains; k++) s += a[k];
+  if (s == 123.456) sink[threadIdx.x & 1023] = s; /* keep the chains alive */
+}
+
+}  // namespace phb
+
+#endif

@@ -1,0 +1,592 @@
+/*
+ * photic_b200.cu -- host side of libphotic_b200.so: the C ABI of include/photic_b200.h.
+ *
+ * Builds the scene-level constants the reference derives in model/samodel.c:505-618 with the HOST
+ * libm (so they are the reference's own bits), stages inputs, runs classify -> solve on the GPU,
+ * and reads the counters back. No CPU fallback: without a CUDA device every compute entry fails.
+ *
+ * Compile: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false  (see build.py)
+ */
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/photic_b200.h"
+#include "../../include/photic_spectra.h"
+#include "device_model.cuh"
+#include "invert_kernel.cuh"
+#include "aux_kernels.cuh"
+
+using namespace phb;
+
+namespace {
+
+thread_local std::string g_last_cuda_error;
+
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) {                                                                       \
+      g_last_cuda_error = std::string(#call) + ": " + cudaGetErrorString(e_);                      \
+      return PHB_ECUDA;                                                                            \
+    }                                                                                              \
+  } while (0)
+
+/* interp_1d, common.c:298-333, including its float-typed bracketing tests. When `bracket` is given
+ * the resolved bracket is returned instead of the value (used for the per-pixel spectra). */
+struct Bracket { int i0, i1, exact; double alpha, oma; };
+
+bool approx_le(float a, float b, float e) { return a < b || approx_equal_f(a, b, e); }
+bool approx_ge(float a, float b, float e) { return a > b || approx_equal_f(a, b, e); }
+
+Bracket resolve_bracket(const double *X, int n, double x) {
+  Bracket B = {0, n > 1 ? 1 : 0, -1, 0.0, 1.0};
+  if (approx_equal_f((float)x, (float)X[0], 1.0e-5f)) { B.exact = 0; return B; }
+  if (approx_equal_f((float)x, (float)X[n - 1], 1.0e-5f)) { B.exact = n - 1; return B; }
+  if (X[0] < X[n - 1] && x < X[0]) { B.i0 = 0; B.i1 = 1; }
+  else if (X[n - 1] > X[0] && x > X[n - 1]) { B.i0 = n - 2; B.i1 = n - 1; }
+  else {
+    for (int i = 0; i < n - 1; i++) {
+      float lo = (float)X[i], hi = (float)X[i + 1], xf = (float)x;
+      if ((approx_le(lo, xf, 1.0e-5f) && approx_ge(hi, xf, 1.0e-5f)) ||
+          (approx_ge(lo, xf, 1.0e-5f) && approx_le(hi, xf, 1.0e-5f))) { B.i0 = i; B.i1 = i + 1; break; }
+    }
+  }
+  volatile double alpha = (x - X[B.i0]) / (X[B.i1] - X[B.i0]);
+  volatile double oma = 1.0 - alpha;
+  B.alpha = alpha; B.oma = oma;
+  return B;
+}
+
+double host_interp_1d(const double *X, const double *Y, int n, double x) {
+  Bracket B = resolve_bracket(X, n, x);
+  if (B.exact >= 0) return Y[B.exact];
+  volatile double t0 = Y[B.i0] * B.oma, t1 = Y[B.i1] * B.alpha; /* no contraction */
+  return t0 + t1;
+}
+
+int validate(const phb_scene_desc *d) {
+  if (!d) return PHB_EINVAL;
+  if (d->n_scenes < 1 || d->n_scenes > PHB_MAX_SCENES) return PHB_EINVAL;
+  for (int s = 0; s < d->n_scenes; s++)
+    if (d->n_bands[s] < 2 || d->n_bands[s] > PHB_MAX_BANDS) return PHB_EINVAL;
+  if (d->n_bottoms < 1 || d->n_bottoms > PHB_MAX_BOTTOMS) return PHB_EINVAL;
+  if (d->n_spatial < 0 || d->n_spatial > PHB_MAX_SPATIAL) return PHB_EINVAL;
+  if (d->n_smoothing_radius < 1 || d->n_smoothing_radius > 8) return PHB_EINVAL;
+  if (d->nrows < 1 || d->ncols < 1 || (long long)d->nrows * d->ncols > 2147483647LL) return PHB_EINVAL;
+  return PHB_OK;
+}
+
+/* samodel.c:505-618 */
+void build_model(const phb_scene_desc *d, ModelConst *M) {
+  memset(M, 0, sizeof(*M));
+  double grid[PH_SPEC_N];
+  for (int i = 0; i < PH_SPEC_N; i++) grid[i] = PH_SPEC_LAMBDA0 + PH_SPEC_DLAMBDA * (double)i;
+  M->n_scenes = d->n_scenes; M->n_bottoms = d->n_bottoms; M->n_spatial = d->n_spatial;
+  M->n_smooth = d->n_smoothing_radius;
+  M->nrows = d->nrows; M->ncols = d->ncols; M->nodata = d->nodata;
+  M->prior_present = d->prior_present; M->prior_nodata = d->prior_nodata;
+  M->aw640 = host_interp_1d(grid, PH_SPEC_AW, PH_SPEC_N, 640.0);
+  const double PI_ = 3.141592653589793;
+  const double targets[4] = {440.0, 490.0, 550.0, 640.0};
+  int sb = 0;
+  for (int s = 0; s < d->n_scenes; s++) {
+    M->n_bands[s] = d->n_bands[s];
+    if (d->n_bands[s] > M->max_bands) M->max_bands = d->n_bands[s];
+    M->sb_begin[s] = sb;
+    volatile double tv = d->theta_view[s], tw = d->theta_sun[s];
+    tv = tv * (PI_ / 180.0); /* samodel.c:538 */
+    tw = tw * (PI_ / 180.0);
+    M->sec_view[s] = 1.0 / cos(tv);
+    M->sec_sun[s] = 1.0 / cos(tw);
+    double lam[PHB_MAX_BANDS];
+    for (int b = 0; b < d->n_bands[s]; b++, sb++) {
+      const double w = (double)d->wavelengths[s][b];
+      lam[b] = w;
+      M->s_of[sb] = s;
+      M->a0[sb] = host_interp_1d(grid, PH_SPEC_A0, PH_SPEC_N, w);
+      M->a1[sb] = host_interp_1d(grid, PH_SPEC_A1, PH_SPEC_N, w);
+      M->bbw[sb] = host_interp_1d(grid, PH_SPEC_BBW, PH_SPEC_N, w);
+      M->aw[sb] = host_interp_1d(grid, PH_SPEC_AW, PH_SPEC_N, w);
+      for (int k = 0; k < d->n_bottoms; k++) M->bottom[k][sb] = host_interp_1d(grid, PH_SPEC_BOTTOM[k], PH_SPEC_N, w);
+      volatile double arg = -0.015 * (w - 440.0); /* -S*(lambda - 440.0), samodel.c:2891 */
+      M->agexp[sb] = exp(arg);
+      M->ratio440[sb] = 440.0 / w;
+    }
+    for (int g = 0; g < 4; g++) {
+      Bracket B = resolve_bracket(lam, d->n_bands[s], targets[g]);
+      M->ib0[s][g] = B.i0; M->ib1[s][g] = B.i1; M->iexact[s][g] = B.exact;
+      M->ialpha[s][g] = B.alpha; M->ioma[s][g] = B.oma;
+    }
+  }
+  M->sb_begin[d->n_scenes] = sb;
+  M->SB = sb;
+}
+
+template <class T>
+struct DevBuf {
+  T *p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaMalloc(&p, n * sizeof(T));
+    if (e == cudaSuccess) cap = n;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+}  // namespace
+
+struct phb_ctx {
+  int device = 0;
+  int n_sm = 0;
+  size_t smem_optin = 0;
+  size_t l2_bytes = 0;
+  ModelConst *d_model = nullptr;
+  unsigned long long *d_exp_tab = nullptr;
+  double *d_log_tab = nullptr, *d_pow_tab = nullptr;
+  DevBuf<int> q_shallow, q_deep, queue;
+  int *d_scalars = nullptr;              /* [0] n_shallow [1] n_deep [2] n_queue [3] head */
+  unsigned long long *d_counters = nullptr; /* 4 counters */
+  double *d_flops = nullptr;
+  DevBuf<double> slabs;
+  /* host entry staging */
+  DevBuf<float> planes, prior, outs;
+  DevBuf<unsigned char> conv;
+  DevBuf<int> nev;
+  DevBuf<double> dbg_rec;
+  DevBuf<int> dbg_pix, dbg_iters;
+  cudaEvent_t ev[4];
+};
+
+extern "C" {
+
+int phb_version(void) { return 100; }
+
+const char *phb_error_string(int code) {
+  switch (code) {
+    case PHB_OK: return "ok";
+    case PHB_EINVAL: return "invalid argument or scene descriptor";
+    case PHB_ENODEVICE: return "no usable CUDA device (photic_b200 has no CPU fallback)";
+    case PHB_ECUDA: return g_last_cuda_error.c_str();
+    case PHB_ENOMEM: return "out of memory";
+    default: return "unknown error";
+  }
+}
+
+int phb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+int phb_band_tables(const phb_scene_desc *desc, double *out_tables, double *out_aux) {
+  int rc = validate(desc);
+  if (rc) return rc;
+  ModelConst M;
+  build_model(desc, &M);
+  const int stride = 4 + PHB_MAX_BOTTOMS;
+  for (int s = 0; s < M.n_scenes; s++)
+    for (int b = 0; b < M.n_bands[s]; b++) {
+      double *o = out_tables + ((size_t)s * PHB_MAX_BANDS + b) * stride;
+      const int sb = M.sb_begin[s] + b;
+      o[0] = M.a0[sb]; o[1] = M.a1[sb]; o[2] = M.aw[sb]; o[3] = M.bbw[sb];
+      for (int k = 0; k < PHB_MAX_BOTTOMS; k++) o[4 + k] = k < M.n_bottoms ? M.bottom[k][sb] : 0.0;
+    }
+  int o = 0;
+  out_aux[o++] = M.aw640;
+  for (int s = 0; s < M.n_scenes; s++) out_aux[o++] = M.sec_view[s];
+  for (int s = 0; s < M.n_scenes; s++) out_aux[o++] = M.sec_sun[s];
+  return PHB_OK;
+}
+
+int phb_ctx_create(int device, phb_ctx **out) {
+  if (!out) return PHB_EINVAL;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return PHB_ENODEVICE;
+  CK(cudaSetDevice(device));
+  phb_ctx *c = new phb_ctx();
+  c->device = device;
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  c->n_sm = prop.multiProcessorCount;
+  c->smem_optin = prop.sharedMemPerBlockOptin;
+  c->l2_bytes = prop.l2CacheSize;
+  static const unsigned long long exp_tab[2 * PHM_N] = PHM_EXP_TAB;
+  static const double log_tab[2 * PHM_N] = PHM_LOG_TAB;
+  static const double pow_tab[3 * PHM_N] = PHM_POWLOG_TAB;
+  CK(cudaMalloc(&c->d_model, sizeof(ModelConst)));
+  CK(cudaMalloc(&c->d_exp_tab, sizeof(exp_tab)));
+  CK(cudaMalloc(&c->d_log_tab, sizeof(log_tab)));
+  CK(cudaMalloc(&c->d_pow_tab, sizeof(pow_tab)));
+  CK(cudaMemcpy(c->d_exp_tab, exp_tab, sizeof(exp_tab), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(c->d_log_tab, log_tab, sizeof(log_tab), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(c->d_pow_tab, pow_tab, sizeof(pow_tab), cudaMemcpyHostToDevice));
+  CK(cudaMalloc(&c->d_scalars, 4 * sizeof(int)));
+  CK(cudaMalloc(&c->d_counters, 4 * sizeof(unsigned long long)));
+  CK(cudaMalloc(&c->d_flops, sizeof(double)));
+  for (int i = 0; i < 4; i++) CK(cudaEventCreate(&c->ev[i]));
+  *out = c;
+  return PHB_OK;
+}
+
+void phb_ctx_destroy(phb_ctx *c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaFree(c->d_model); cudaFree(c->d_exp_tab); cudaFree(c->d_log_tab); cudaFree(c->d_pow_tab);
+  cudaFree(c->d_scalars); cudaFree(c->d_counters); cudaFree(c->d_flops);
+  c->q_shallow.release(); c->q_deep.release(); c->queue.release(); c->slabs.release();
+  c->planes.release(); c->prior.release(); c->outs.release(); c->conv.release(); c->nev.release();
+  c->dbg_rec.release(); c->dbg_pix.release(); c->dbg_iters.release();
+  for (int i = 0; i < 4; i++) cudaEventDestroy(c->ev[i]);
+  delete c;
+}
+
+int phb_debug_record_len(const phb_scene_desc *d) {
+  if (validate(d)) return 0;
+  int mb = 0;
+  for (int s = 0; s < d->n_scenes; s++) mb = d->n_bands[s] > mb ? d->n_bands[s] : mb;
+  return kRecHead + d->n_scenes * mb + 3 * d->n_scenes;
+}
+
+static int invert_device_impl(phb_ctx *c, const phb_scene_desc *desc, const float *d_planes, const float *d_prior,
+                              int row_begin, int row_end, const phb_outputs *d_out, cudaStream_t st, phb_stats *stats,
+                              double *d_rec, int *d_pix, int *d_iters, long long dbg_cap) {
+  if (!c || !d_planes || !d_out) return PHB_EINVAL;
+  int rc = validate(desc);
+  if (rc) return rc;
+  if (row_begin < 0 || row_end > desc->nrows || row_begin >= row_end) return PHB_EINVAL;
+  CK(cudaSetDevice(c->device));
+  ModelConst M;
+  build_model(desc, &M);
+  CK(cudaMemcpyAsync(c->d_model, &M, sizeof(M), cudaMemcpyHostToDevice, st));
+  const size_t npx = (size_t)(row_end - row_begin) * desc->ncols;
+  CK(c->q_shallow.ensure(npx)); CK(c->q_deep.ensure(npx)); CK(c->queue.ensure(npx));
+  CK(cudaMemsetAsync(c->d_scalars, 0, 4 * sizeof(int), st));
+  CK(cudaMemsetAsync(c->d_counters, 0, 4 * sizeof(unsigned long long), st));
+  CK(cudaMemsetAsync(c->d_flops, 0, sizeof(double), st));
+
+  /* classification pre-pass */
+  ClassifyParams cp;
+  cp.M = c->d_model; cp.planes = d_planes; cp.prior = desc->prior_present ? d_prior : nullptr;
+  cp.row_begin = row_begin; cp.row_end = row_end;
+  cp.queue_shallow = c->q_shallow.p; cp.queue_deep = c->q_deep.p;
+  cp.n_shallow = c->d_scalars + 0; cp.n_deep = c->d_scalars + 1;
+  cp.out = *d_out;
+  CK(cudaEventRecord(c->ev[0], st));
+  classify_kernel<<<c->n_sm * 8, 256, 0, st>>>(cp);
+  concat_queue_kernel<<<c->n_sm * 4, 256, 0, st>>>(c->q_shallow.p, c->q_deep.p, c->d_scalars + 0, c->d_scalars + 1,
+                                                    c->queue.p, c->d_scalars + 2);
+  CK(cudaEventRecord(c->ev[1], st));
+  CK(cudaGetLastError());
+
+  /* solve */
+  const int nsp = M.n_spatial == 0 ? 1 : M.n_spatial;
+  const int NrMax = (2 * nsp - 1) * (2 * nsp - 1);
+  SolveParams sp;
+  sp.L = make_layout(M.SB, M.n_scenes, M.n_bottoms, NrMax);
+  const long long slab_doubles = (long long)(sp.L.nmax + 1) * sp.L.nmax + sp.L.nmax + sp.L.Tmax;
+  int W_smem = (int)(((long long)c->smem_optin - sp.L.cta_bytes) / sp.L.warp_bytes);
+  /* keep the simplex slabs of all resident warps inside ~3/4 of L2 (they are re-read every iteration) */
+  int W_l2 = (int)((c->l2_bytes * 3 / 4) / ((size_t)c->n_sm * slab_doubles * 8));
+  int W = W_smem < W_l2 ? W_smem : W_l2;
+  if (W > 16) W = 16;
+  cudaFuncAttributes fa0;
+  CK(cudaFuncGetAttributes(&fa0, solve_kernel));
+  const int W_reg = 65536 / (((fa0.numRegs + 7) / 8 * 8) * 32); /* register file: 64K x 32 bit per SM */
+  if (W > W_reg) W = W_reg;
+  if (const char *e = getenv("PHB_WARPS_PER_CTA")) { int v = atoi(e); if (v >= 1 && v <= W_smem && v <= W_reg) W = v; }
+  if (W < 1) W = 1;
+  if (W_smem < 1) return PHB_EINVAL; /* configuration does not fit shared memory */
+  int ctas = c->n_sm;
+  if (const char *e = getenv("PHB_CTAS")) { int v = atoi(e); if (v >= 1) ctas = v; }
+  const size_t smem = (size_t)sp.L.cta_bytes + (size_t)W * sp.L.warp_bytes;
+  CK(c->slabs.ensure((size_t)ctas * W * slab_doubles));
+  sp.M = c->d_model; sp.planes = d_planes; sp.prior = cp.prior;
+  sp.queue = c->queue.p; sp.n_queue = c->d_scalars + 2; sp.head = c->d_scalars + 3;
+  sp.slabs = c->slabs.p; sp.slab_stride = slab_doubles;
+  sp.out = *d_out;
+  sp.dbg_rec = d_rec; sp.dbg_pix = d_pix; sp.dbg_iters = d_iters; sp.reclen = phb_debug_record_len(desc);
+  sp.dbg_capacity = dbg_cap;
+  sp.counters = c->d_counters; sp.flops = c->d_flops;
+  sp.exp_tab = c->d_exp_tab; sp.log_tab = c->d_log_tab; sp.pow_tab = c->d_pow_tab;
+  CK(cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CK(cudaEventRecord(c->ev[2], st));
+  solve_kernel<<<ctas, W * 32, smem, st>>>(sp);
+  CK(cudaEventRecord(c->ev[3], st));
+  CK(cudaGetLastError());
+
+  if (stats) {
+    unsigned long long cnt[4];
+    int sc[4];
+    double fl;
+    CK(cudaMemcpyAsync(cnt, c->d_counters, sizeof(cnt), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(sc, c->d_scalars, sizeof(sc), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&fl, c->d_flops, sizeof(fl), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    memset(stats, 0, sizeof(*stats));
+    stats->n_valid = sc[2]; stats->n_shallow = sc[0];
+    stats->n_evals = (int64_t)cnt[0]; stats->n_iters = (int64_t)cnt[1]; stats->n_converged = (int64_t)cnt[2];
+    stats->alg_flops = fl;
+    CK(cudaEventElapsedTime(&stats->ms_classify, c->ev[0], c->ev[1]));
+    CK(cudaEventElapsedTime(&stats->ms_solve, c->ev[2], c->ev[3]));
+    stats->warps_per_cta = W; stats->ctas = ctas; stats->smem_bytes = (int)smem;
+    cudaFuncAttributes fa;
+    CK(cudaFuncGetAttributes(&fa, solve_kernel));
+    stats->regs = fa.numRegs;
+  }
+  return PHB_OK;
+}
+
+int phb_invert_device(phb_ctx *ctx, const phb_scene_desc *desc, const float *d_planes, const float *d_prior,
+                      int row_begin, int row_end, const phb_outputs *d_out, void *stream, phb_stats *stats) {
+  return invert_device_impl(ctx, desc, d_planes, d_prior, row_begin, row_end, d_out, (cudaStream_t)stream, stats,
+                            nullptr, nullptr, nullptr, 0);
+}
+
+static int invert_host_impl(phb_ctx *c, const phb_scene_desc *desc, const float *const *h_planes, const float *h_prior,
+                            int row_begin, int row_end, const phb_outputs *h_out, phb_stats *stats, double *rec,
+                            int32_t *pix, int32_t *iters, int64_t capacity) {
+  if (!c || !h_planes || !h_out) return PHB_EINVAL;
+  int rc = validate(desc);
+  if (rc) return rc;
+  if (row_begin < 0 || row_end > desc->nrows || row_begin >= row_end) return PHB_EINVAL;
+  CK(cudaSetDevice(c->device));
+  int SB = 0, mb = 0;
+  for (int s = 0; s < desc->n_scenes; s++) { SB += desc->n_bands[s]; mb = desc->n_bands[s] > mb ? desc->n_bands[s] : mb; }
+  const size_t px = (size_t)desc->nrows * desc->ncols;
+  const int Ns = desc->n_scenes;
+  cudaStream_t st = 0;
+  cudaEvent_t e0, e1, e2, e3;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1)); CK(cudaEventCreate(&e2)); CK(cudaEventCreate(&e3));
+  CK(c->planes.ensure(px * SB));
+  CK(cudaEventRecord(e0, st));
+  for (int g = 0; g < SB; g++)
+    CK(cudaMemcpyAsync(c->planes.p + g * px, h_planes[g], px * sizeof(float), cudaMemcpyHostToDevice, st));
+  const bool use_prior = desc->prior_present && h_prior;
+  if (use_prior) {
+    CK(c->prior.ensure(px));
+    CK(cudaMemcpyAsync(c->prior.p, h_prior, px * sizeof(float), cudaMemcpyHostToDevice, st));
+  }
+  CK(cudaEventRecord(e1, st));
+  /* device output planes: 9 scalar grids, K, P, G, X */
+  const size_t n_out_planes = 9 + (size_t)Ns * mb + 3 * (size_t)Ns;
+  CK(c->outs.ensure(n_out_planes * px));
+  CK(c->conv.ensure(px)); CK(c->nev.ensure(px));
+  phb_outputs d;
+  float *o = c->outs.p;
+  float **slots[9] = {&d.depth, &d.model_error, &d.bottom_albedo, &d.bottom_sand, &d.bottom_seagrass, &d.bottom_coral,
+                      &d.K_min, &d.bottom_type, &d.index_optical_depth};
+  float *const hslots[9] = {h_out->depth, h_out->model_error, h_out->bottom_albedo, h_out->bottom_sand,
+                            h_out->bottom_seagrass, h_out->bottom_coral, h_out->K_min, h_out->bottom_type,
+                            h_out->index_optical_depth};
+  for (int k = 0; k < 9; k++) { *slots[k] = hslots[k] ? o : nullptr; o += px; }
+  d.K = h_out->K ? o : nullptr; o += (size_t)Ns * mb * px;
+  d.P = h_out->P ? o : nullptr; o += (size_t)Ns * px;
+  d.G = h_out->G ? o : nullptr; o += (size_t)Ns * px;
+  d.X = h_out->X ? o : nullptr; o += (size_t)Ns * px;
+  d.converged = h_out->converged ? c->conv.p : nullptr;
+  d.n_evals = h_out->n_evals ? c->nev.p : nullptr;
+  double *d_rec = nullptr; int *d_pix = nullptr, *d_it = nullptr;
+  const int reclen = phb_debug_record_len(desc);
+  if (rec && capacity > 0) {
+    CK(c->dbg_rec.ensure((size_t)capacity * reclen)); CK(c->dbg_pix.ensure(capacity)); CK(c->dbg_iters.ensure(2 * capacity));
+    CK(cudaMemsetAsync(c->dbg_pix.p, 0xff, capacity * sizeof(int), st));
+    d_rec = c->dbg_rec.p; d_pix = c->dbg_pix.p; d_it = c->dbg_iters.p;
+  }
+  phb_stats local;
+  phb_scene_desc dd = *desc;
+  dd.prior_present = use_prior ? 1 : 0;
+  rc = invert_device_impl(c, &dd, c->planes.p, use_prior ? c->prior.p : nullptr, row_begin, row_end, &d, st, &local, d_rec,
+                          d_pix, d_it, capacity);
+  if (rc) return rc;
+  /* copy back only the rows that were inverted */
+  const size_t a = (size_t)row_begin * desc->ncols, nb = (size_t)(row_end - row_begin) * desc->ncols;
+  CK(cudaEventRecord(e2, st));
+  for (int k = 0; k < 9; k++)
+    if (hslots[k]) CK(cudaMemcpyAsync(hslots[k] + a, *slots[k] + a, nb * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (h_out->K)
+    for (int q = 0; q < Ns * mb; q++)
+      CK(cudaMemcpyAsync(h_out->K + q * px + a, d.K + q * px + a, nb * sizeof(float), cudaMemcpyDeviceToHost, st));
+  float *const hpgx[3] = {h_out->P, h_out->G, h_out->X};
+  float *const dpgx[3] = {d.P, d.G, d.X};
+  for (int v = 0; v < 3; v++)
+    if (hpgx[v])
+      for (int s = 0; s < Ns; s++)
+        CK(cudaMemcpyAsync(hpgx[v] + s * px + a, dpgx[v] + s * px + a, nb * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (h_out->converged) CK(cudaMemcpyAsync(h_out->converged + a, c->conv.p + a, nb, cudaMemcpyDeviceToHost, st));
+  if (h_out->n_evals) CK(cudaMemcpyAsync(h_out->n_evals + a, c->nev.p + a, nb * sizeof(int), cudaMemcpyDeviceToHost, st));
+  if (d_rec) {
+    CK(cudaMemcpyAsync(rec, d_rec, (size_t)capacity * reclen * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(pix, d_pix, capacity * sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (iters) CK(cudaMemcpyAsync(iters, d_it, 2 * capacity * sizeof(int), cudaMemcpyDeviceToHost, st));
+  }
+  CK(cudaEventRecord(e3, st));
+  CK(cudaStreamSynchronize(st));
+  CK(cudaEventElapsedTime(&local.ms_h2d, e0, e1));
+  CK(cudaEventElapsedTime(&local.ms_d2h, e2, e3));
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); cudaEventDestroy(e3);
+  if (stats) *stats = local;
+  return PHB_OK;
+}
+
+int phb_invert_host(phb_ctx *ctx, const phb_scene_desc *desc, const float *const *h_planes, const float *h_prior,
+                    int row_begin, int row_end, const phb_outputs *h_out, phb_stats *stats) {
+  return invert_host_impl(ctx, desc, h_planes, h_prior, row_begin, row_end, h_out, stats, nullptr, nullptr, nullptr, 0);
+}
+
+int phb_invert_host_debug(phb_ctx *ctx, const phb_scene_desc *desc, const float *const *h_planes, const float *h_prior,
+                          int row_begin, int row_end, const phb_outputs *h_out, double *rec, int32_t *pix,
+                          int32_t *n_iters, int64_t capacity, phb_stats *stats) {
+  return invert_host_impl(ctx, desc, h_planes, h_prior, row_begin, row_end, h_out, stats, rec, pix, n_iters, capacity);
+}
+
+/* ---- known-answer hooks ----------------------------------------------------------------------- */
+
+int phb_kat_objective(phb_ctx *c, const phb_scene_desc *desc, int nb_active, int n_regions, int origin,
+                      const double *rrs_measured, int nparams, int nvec, const double *params, double *out6) {
+  if (!c) return PHB_EINVAL;
+  int rc = validate(desc);
+  if (rc) return rc;
+  CK(cudaSetDevice(c->device));
+  ModelConst M;
+  phb_scene_desc dd = *desc;
+  dd.n_bottoms = nb_active;
+  build_model(&dd, &M);
+  CK(cudaMemcpy(c->d_model, &M, sizeof(M), cudaMemcpyHostToDevice));
+  SolveParams sp;
+  memset(&sp, 0, sizeof(sp));
+  sp.L = make_layout(M.SB, M.n_scenes, nb_active, n_regions);
+  if (nparams != sp.L.nmax) return PHB_EINVAL;
+  const long long slab_doubles = (long long)(sp.L.nmax + 1) * sp.L.nmax + sp.L.nmax + sp.L.Tmax;
+  CK(c->slabs.ensure(slab_doubles));
+  sp.M = c->d_model; sp.slabs = c->slabs.p; sp.slab_stride = slab_doubles;
+  sp.exp_tab = c->d_exp_tab; sp.log_tab = c->d_log_tab; sp.pow_tab = c->d_pow_tab;
+  double *d_meas, *d_par, *d_out;
+  const size_t nm = (size_t)n_regions * M.SB;
+  /* rrs_measured arrives [n_regions][n_scenes][max_bands]; flatten to [n_regions][SB] */
+  std::vector<double> flat(nm);
+  for (int r = 0; r < n_regions; r++)
+    for (int s = 0; s < M.n_scenes; s++)
+      for (int b = 0; b < M.n_bands[s]; b++)
+        flat[(size_t)r * M.SB + M.sb_begin[s] + b] = rrs_measured[((size_t)r * M.n_scenes + s) * M.max_bands + b];
+  CK(cudaMalloc(&d_meas, nm * 8)); CK(cudaMalloc(&d_par, (size_t)nvec * nparams * 8)); CK(cudaMalloc(&d_out, (size_t)nvec * 6 * 8));
+  CK(cudaMemcpy(d_meas, flat.data(), nm * 8, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_par, params, (size_t)nvec * nparams * 8, cudaMemcpyHostToDevice));
+  const size_t smem = (size_t)sp.L.cta_bytes + sp.L.warp_bytes;
+  CK(cudaFuncSetAttribute(kat_objective_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kat_objective_kernel<<<1, 32, smem>>>(sp, nb_active, n_regions, origin, d_meas, nvec, d_par, d_out);
+  CK(cudaGetLastError());
+  CK(cudaMemcpy(out6, d_out, (size_t)nvec * 6 * 8, cudaMemcpyDeviceToHost));
+  cudaFree(d_meas); cudaFree(d_par); cudaFree(d_out);
+  return PHB_OK;
+}
+
+int phb_kat_math(phb_ctx *c, int fn, const double *x, const double *y, int64_t n, double *out) {
+  if (!c || !x || !out || n <= 0 || fn < 0 || fn > 2 || (fn == 2 && !y)) return PHB_EINVAL;
+  CK(cudaSetDevice(c->device));
+  double *dx, *dy = nullptr, *dout;
+  CK(cudaMalloc(&dx, n * 8)); CK(cudaMalloc(&dout, n * 8));
+  CK(cudaMemcpy(dx, x, n * 8, cudaMemcpyHostToDevice));
+  if (fn == 2) { CK(cudaMalloc(&dy, n * 8)); CK(cudaMemcpy(dy, y, n * 8, cudaMemcpyHostToDevice)); }
+  kat_math_kernel<<<c->n_sm * 4, 256>>>(fn, dx, dy, (long long)n, dout, c->d_exp_tab, c->d_log_tab, c->d_pow_tab);
+  CK(cudaGetLastError());
+  CK(cudaMemcpy(out, dout, n * 8, cudaMemcpyDeviceToHost));
+  cudaFree(dx); cudaFree(dout); if (dy) cudaFree(dy);
+  return PHB_OK;
+}
+
+/* ---- REFINE ------------------------------------------------------------------------------------- */
+
+int phb_refine_minmax_device(phb_ctx *c, const float *d_in, int64_t n, float nodata, float *h_minmax, void *stream) {
+  if (!c || !d_in || !h_minmax || n <= 0) return PHB_EINVAL;
+  CK(cudaSetDevice(c->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned int init[2] = {0xffffffffu, 0u}; /* ordered-uint encodings of +max / -max */
+  unsigned int *d_mm = reinterpret_cast<unsigned int *>(c->d_counters);
+  CK(cudaMemcpyAsync(d_mm, init, sizeof(init), cudaMemcpyHostToDevice, st));
+  refine_minmax_kernel<<<c->n_sm * 4, 256, 0, st>>>(d_in, (long long)n, nodata, d_mm);
+  CK(cudaGetLastError());
+  unsigned int mm[2];
+  CK(cudaMemcpyAsync(mm, d_mm, sizeof(mm), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  h_minmax[0] = mm[0] == 0xffffffffu ? 1.0e10f : ordered_to_float(mm[0]);   /* BIG, common.c:1228 */
+  h_minmax[1] = mm[1] == 0u ? -1.0e10f : ordered_to_float(mm[1]);
+  return PHB_OK;
+}
+
+int phb_refine_device(phb_ctx *c, const float *d_in, float nodata, const float *d_land, float land_nodata,
+                      const float *d_shallow, float shallow_nodata, int64_t n, int flags, const float *args,
+                      const float *minmax, float *d_out, void *stream) {
+  if (!c || !d_in || !d_out || !args || n <= 0) return PHB_EINVAL;
+  if (!(flags & PHB_REFINE_CLIP) && !minmax) return PHB_EINVAL;
+  CK(cudaSetDevice(c->device));
+  RefineParams rp = make_refine_params(flags, args, minmax);
+  rp.in = d_in; rp.land = d_land; rp.shallow = d_shallow; rp.out = d_out; rp.n = (long long)n;
+  rp.nodata = nodata; rp.land_nodata = land_nodata; rp.shallow_nodata = shallow_nodata;
+  rp.exp_tab = c->d_exp_tab; rp.log_tab = c->d_log_tab; rp.pow_tab = c->d_pow_tab;
+  refine_kernel<<<c->n_sm * 8, 256, 0, (cudaStream_t)stream>>>(rp);
+  CK(cudaGetLastError());
+  return PHB_OK;
+}
+
+int phb_refine_host(phb_ctx *c, const float *h_in, float nodata, const float *h_land, float land_nodata,
+                    const float *h_shallow, float shallow_nodata, int nrows, int ncols, int flags, const float *args,
+                    float *h_out) {
+  if (!c || !h_in || !h_out || !args || nrows < 1 || ncols < 1) return PHB_EINVAL;
+  CK(cudaSetDevice(c->device));
+  const size_t n = (size_t)nrows * ncols;
+  CK(c->outs.ensure(4 * n));
+  float *d_in = c->outs.p, *d_land = d_in + n, *d_sh = d_land + n, *d_out = d_sh + n;
+  CK(cudaMemcpy(d_in, h_in, n * 4, cudaMemcpyHostToDevice));
+  if (h_land) CK(cudaMemcpy(d_land, h_land, n * 4, cudaMemcpyHostToDevice));
+  if (h_shallow) CK(cudaMemcpy(d_sh, h_shallow, n * 4, cudaMemcpyHostToDevice));
+  float mm[2] = {0, 0};
+  if (!(flags & PHB_REFINE_CLIP)) {
+    int rc = phb_refine_minmax_device(c, d_in, (int64_t)n, nodata, mm, nullptr);
+    if (rc) return rc;
+  }
+  int rc = phb_refine_device(c, d_in, nodata, h_land ? d_land : nullptr, land_nodata, h_shallow ? d_sh : nullptr,
+                             shallow_nodata, (int64_t)n, flags, args, mm, d_out, nullptr);
+  if (rc) return rc;
+  CK(cudaMemcpy(h_out, d_out, n * 4, cudaMemcpyDeviceToHost));
+  return PHB_OK;
+}
+
+/* ---- FP64 peak ---------------------------------------------------------------------------------- */
+
+int phb_fp64_peak(phb_ctx *c, double *tflops, float *ms) {
+  if (!c || !tflops) return PHB_EINVAL;
+  CK(cudaSetDevice(c->device));
+  double *d_sink;
+  CK(cudaMalloc(&d_sink, sizeof(double) * 1024));
+  const int blocks = c->n_sm * 8, threads = 256, iters = 1 << 14;
+  dfma_peak_kernel<<<blocks, threads>>>(d_sink, 64); /* warm-up */
+  CK(cudaDeviceSynchronize());
+  float best = 1e30f;
+  for (int rep = 0; rep < 5; rep++) {
+    CK(cudaEventRecord(c->ev[0]));
+    dfma_peak_kernel<<<blocks, threads>>>(d_sink, iters);
+    CK(cudaEventRecord(c->ev[1]));
+    CK(cudaEventSynchronize(c->ev[1]));
+    float t;
+    CK(cudaEventElapsedTime(&t, c->ev[0], c->ev[1]));
+    if (t < best) best = t;
+  }
+  CK(cudaGetLastError());
+  const double flops = 2.0 * kPeakChains * (double)iters * blocks * threads;
+  *tflops = flops / (best * 1e-3) / 1e12;
+  if (ms) *ms = best;
+  cudaFree(d_sink);
+  return PHB_OK;
+}
+
+}  /* extern "C" */

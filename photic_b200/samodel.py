@@ -1,0 +1,255 @@
+"""Python host mirror of the reference's inversion entry point (model/samodel.h:8-19).
+
+``Inverter`` owns one device context of libphotic_b200.so; ``samodel()`` keeps the reference's
+argument names and meaning (scene_data / gridded_data / scene_indexes ... -> the ten output grids),
+so the parity tests read like calls into the reference. All compute happens in the CUDA library;
+this module only marshals buffers. torch is used for device memory and streams only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import capi
+from .capi import Outputs, SceneDesc, Stats, SCALAR_PLANES, check
+
+
+def _np_ptr(a, t):
+    return a.ctypes.data_as(t)
+
+
+class Inverter:
+    """One per GPU. ``device`` is the CUDA ordinal. Raises PhoticError when no device is usable."""
+
+    def __init__(self, device: int = 0):
+        self.lib = capi.lib()
+        self.ctx = C.c_void_p()
+        check(self.lib.phb_ctx_create(int(device), C.byref(self.ctx)))
+        self.device = device
+
+    def close(self):
+        if self.ctx:
+            self.lib.phb_ctx_destroy(self.ctx)
+            self.ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- host buffers (what the samodel() shim uses) ---------------------------------------------
+    def _host_outputs(self, desc: SceneDesc, want_scene_planes: bool, buffers: dict | None):
+        nrows, ncols, ns = desc.nrows, desc.ncols, desc.n_scenes
+        mb = max(desc.n_bands[s] for s in range(ns))
+        out = buffers if buffers is not None else {}
+        o = Outputs()
+        for name in SCALAR_PLANES:
+            if name not in out:
+                out[name] = np.zeros((nrows, ncols), dtype=np.float32)
+            setattr(o, name, _np_ptr(out[name], capi._fp))
+        if want_scene_planes:
+            shapes = {"K": (ns, mb, nrows, ncols), "P": (ns, nrows, ncols), "G": (ns, nrows, ncols),
+                      "X": (ns, nrows, ncols)}
+            for name, shp in shapes.items():
+                if name not in out:
+                    out[name] = np.zeros(shp, dtype=np.float32)
+                setattr(o, name, _np_ptr(out[name], capi._fp))
+        if "converged" not in out:
+            out["converged"] = np.zeros((nrows, ncols), dtype=np.uint8)
+        if "n_evals" not in out:
+            out["n_evals"] = np.zeros((nrows, ncols), dtype=np.int32)
+        o.converged = _np_ptr(out["converged"], capi._u8p)
+        o.n_evals = _np_ptr(out["n_evals"], capi._ip)
+        return o, out
+
+    @staticmethod
+    def _plane_ptrs(planes):
+        """planes: ndarray [n_planes, nrows, ncols] float32 (C order) or a list of 2-D arrays."""
+        if isinstance(planes, np.ndarray):
+            assert planes.dtype == np.float32 and planes.flags["C_CONTIGUOUS"]
+            lst = [planes[g] for g in range(planes.shape[0])]
+        else:
+            lst = [np.ascontiguousarray(p, dtype=np.float32) for p in planes]
+        arr = (C.c_void_p * len(lst))(*[p.ctypes.data for p in lst])
+        return arr, lst
+
+    def invert_host(self, desc: SceneDesc, planes, prior, row_begin=0, row_end=None, scene_planes=True,
+                    buffers=None, debug=False):
+        """Inverts rows [row_begin,row_end) from host arrays; returns (outputs dict, stats dict)."""
+        row_end = desc.nrows if row_end is None else row_end
+        ptrs, keep = self._plane_ptrs(planes)
+        pr = None if prior is None else np.ascontiguousarray(prior, dtype=np.float32)
+        o, out = self._host_outputs(desc, scene_planes, buffers)
+        st = Stats()
+        prp = C.c_void_p(None) if pr is None else C.c_void_p(pr.ctypes.data)
+        if not debug:
+            check(self.lib.phb_invert_host(self.ctx, C.byref(desc), ptrs, prp, row_begin, row_end, C.byref(o), C.byref(st)))
+        else:
+            cap = (row_end - row_begin) * desc.ncols
+            rl = self.lib.phb_debug_record_len(C.byref(desc))
+            rec = np.zeros((cap, rl))
+            pix = np.full(cap, -1, dtype=np.int32)
+            it = np.zeros((cap, 2), dtype=np.int32)
+            check(self.lib.phb_invert_host_debug(self.ctx, C.byref(desc), ptrs, prp, row_begin, row_end, C.byref(o),
+                                                 _np_ptr(rec, capi._dp), _np_ptr(pix, capi._ip), _np_ptr(it, capi._ip),
+                                                 cap, C.byref(st)))
+            n = int(st.n_valid)
+            order = np.argsort(pix[:n], kind="stable")
+            out["rec"], out["pix"] = rec[:n][order], pix[:n][order]
+            out["rec_evals"] = it[:n, 0][order]
+            out["rec_converged"] = (it[:n, 1] & 1)[order]
+            out["rec_iters"] = (it[:n, 1] >> 1)[order]
+        return out, st.as_dict()
+
+    # ---- device buffers (resident data: bench `value`, multi-GPU shards) ---------------------------
+    def invert_device(self, desc: SceneDesc, planes, prior, outputs: dict, row_begin=0, row_end=None, stream=None):
+        """planes / prior / outputs are torch CUDA tensors on this device. Returns stats dict."""
+        import torch
+
+        row_end = desc.nrows if row_end is None else row_end
+        o = Outputs()
+        for name in SCALAR_PLANES + ("K", "P", "G", "X"):
+            t = outputs.get(name)
+            if t is not None:
+                assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
+                setattr(o, name, C.cast(t.data_ptr(), capi._fp))
+        if outputs.get("converged") is not None:
+            o.converged = C.cast(outputs["converged"].data_ptr(), capi._u8p)
+        if outputs.get("n_evals") is not None:
+            o.n_evals = C.cast(outputs["n_evals"].data_ptr(), capi._ip)
+        st = Stats()
+        s = torch.cuda.current_stream(planes.device) if stream is None else stream
+        assert planes.is_cuda and planes.dtype == torch.float32 and planes.is_contiguous()
+        prp = C.c_void_p(None) if prior is None else C.c_void_p(prior.data_ptr())
+        check(self.lib.phb_invert_device(self.ctx, C.byref(desc), C.c_void_p(planes.data_ptr()), prp, row_begin, row_end,
+                                         C.byref(o), C.c_void_p(s.cuda_stream), C.byref(st)))
+        return st.as_dict()
+
+    @staticmethod
+    def alloc_device_outputs(desc: SceneDesc, device, scene_planes=True):
+        import torch
+
+        nrows, ncols, ns = desc.nrows, desc.ncols, desc.n_scenes
+        mb = max(desc.n_bands[s] for s in range(ns))
+        out = {n: torch.zeros((nrows, ncols), dtype=torch.float32, device=device) for n in SCALAR_PLANES}
+        if scene_planes:
+            out["K"] = torch.zeros((ns, mb, nrows, ncols), dtype=torch.float32, device=device)
+            for n in ("P", "G", "X"):
+                out[n] = torch.zeros((ns, nrows, ncols), dtype=torch.float32, device=device)
+        out["converged"] = torch.zeros((nrows, ncols), dtype=torch.uint8, device=device)
+        out["n_evals"] = torch.zeros((nrows, ncols), dtype=torch.int32, device=device)
+        return out
+
+    # ---- known-answer hooks --------------------------------------------------------------------------
+    def kat_objective(self, desc: SceneDesc, nb_active, n_regions, origin, meas, params):
+        meas = np.ascontiguousarray(meas, dtype=np.float64)
+        params = np.ascontiguousarray(params, dtype=np.float64)
+        nvec, npar = params.shape
+        out = np.zeros((nvec, 6))
+        check(self.lib.phb_kat_objective(self.ctx, C.byref(desc), nb_active, n_regions, origin, _np_ptr(meas, capi._dp),
+                                         npar, nvec, _np_ptr(params, capi._dp), _np_ptr(out, capi._dp)))
+        return out
+
+    def kat_math(self, fn: int, x, y=None):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        out = np.zeros_like(x)
+        yp = C.cast(None, capi._dp)
+        if y is not None:
+            y = np.ascontiguousarray(y, dtype=np.float64)
+            yp = _np_ptr(y, capi._dp)
+        check(self.lib.phb_kat_math(self.ctx, fn, _np_ptr(x, capi._dp), yp, x.size, _np_ptr(out, capi._dp)))
+        return out
+
+    def fp64_peak(self):
+        t, ms = C.c_double(0), C.c_float(0)
+        check(self.lib.phb_fp64_peak(self.ctx, C.byref(t), C.byref(ms)))
+        return t.value, ms.value
+
+    # ---- REFINE ----------------------------------------------------------------------------------------
+    def refine_host(self, grid, nodata, flags, args, land=None, land_nodata=-9999.0, shallow=None,
+                    shallow_nodata=-9999.0):
+        g = np.ascontiguousarray(grid, dtype=np.float32)
+        out = np.zeros_like(g)
+        a = np.ascontiguousarray(args, dtype=np.float32)
+        ld = None if land is None else np.ascontiguousarray(land, dtype=np.float32)
+        sh = None if shallow is None else np.ascontiguousarray(shallow, dtype=np.float32)
+        null = C.cast(None, capi._fp)
+        check(self.lib.phb_refine_host(self.ctx, _np_ptr(g, capi._fp), nodata, null if ld is None else _np_ptr(ld, capi._fp),
+                                       land_nodata, null if sh is None else _np_ptr(sh, capi._fp), shallow_nodata,
+                                       g.shape[0], g.shape[1], flags, _np_ptr(a, capi._fp), _np_ptr(out, capi._fp)))
+        return out
+
+
+# --------------------------------------------------------------------------------------------------
+# The reference's call surface, in Python (model/samodel.h:8-19, model/common.h:69-84,194-218)
+# --------------------------------------------------------------------------------------------------
+
+@dataclass
+class geogrid:
+    """model/common.h:69-84 (fields samodel reads)."""
+    array: np.ndarray
+    nodata_value: float = -9999.0
+    nrows: int = 0
+    ncols: int = 0
+
+    def __post_init__(self):
+        self.nrows, self.ncols = self.array.shape
+
+
+@dataclass
+class scene:
+    """model/common.h:194-218 (fields samodel reads)."""
+    scene_name: str
+    band_indexes: list
+    wavelengths: list  # int nm
+    theta_v: float
+    theta_w: float
+    H_tide: float = 0.0
+    R_sigma: list = field(default_factory=list)
+
+    @property
+    def n_bands(self):
+        return len(self.band_indexes)
+
+
+_default_inverter = None
+
+
+def samodel(scene_data, gridded_data, scene_indexes, nscenes, empirical_depth_present, empirical_depths,
+            n_smoothing_radius, n_spatial, n_bottoms, depth, depth_sigma, model_error, bottom_albedo, bottom_sand,
+            bottom_seagrass, bottom_coral, K_min, bottom_type, index_optical_depth, pagesize=8.0, background=0,
+            linewidth=1, inverter: Inverter | None = None):
+    """Same arguments as the reference's samodel(); the ten output grids are filled in place.
+
+    Differences from the reference, all documented in DESIGN.md: every valid pixel is inverted from
+    a cold start (no LUT / hot start, which make the reference order dependent); depth_sigma is
+    left at 0 (its Monte-Carlo pass is seeded by time(NULL) in the reference).
+    Returns the stats dict (the reference returns nothing).
+    """
+    global _default_inverter
+    inv = inverter
+    if inv is None:
+        if _default_inverter is None:
+            _default_inverter = Inverter(0)
+        inv = _default_inverter
+    scs = [scene_data[scene_indexes[k]] for k in range(nscenes)]
+    g0 = gridded_data[scs[0].band_indexes[0]]
+    desc = capi.make_desc(np.array([s.wavelengths for s in scs], dtype=np.int32), [s.theta_v for s in scs],
+                          [s.theta_w for s in scs], [s.H_tide for s in scs], g0.nrows, g0.ncols,
+                          nodata=g0.nodata_value, prior_present=bool(empirical_depth_present),
+                          prior_nodata=empirical_depths.nodata_value if empirical_depth_present else -9999.0,
+                          n_smooth=n_smoothing_radius, n_spatial=n_spatial, n_bottoms=n_bottoms)
+    planes = [gridded_data[k].array for s in scs for k in s.band_indexes]
+    buffers = {"depth": depth, "model_error": model_error, "bottom_albedo": bottom_albedo, "bottom_sand": bottom_sand,
+               "bottom_seagrass": bottom_seagrass, "bottom_coral": bottom_coral, "K_min": K_min,
+               "bottom_type": bottom_type, "index_optical_depth": index_optical_depth}
+    for v in buffers.values():
+        assert v.dtype == np.float32 and v.flags["C_CONTIGUOUS"]
+    out, stats = inv.invert_host(desc, planes, empirical_depths.array if empirical_depth_present else None,
+                                 buffers=buffers)
+    depth_sigma[...] = 0.0
+    samodel.last_outputs = out
+    return stats
