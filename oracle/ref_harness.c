@@ -111,9 +111,11 @@ static model_data *make_md(const ref_cfg *c) {
   md->a_w640 = interp_1d(ref_wlens, aw_Pope_Fry1997, n_ref_wlens, 640.0);
   for (s = 0; s < c->nscenes; s++) {
     md->H_tide[s] = c->h_tide[s];
-    md->theta_view[s] = c->theta_v[s] * PI / 180.0;
+    md->theta_view[s] = c->theta_v[s];
+    md->theta_view[s] *= PI / 180.0; /* exactly as samodel.c:538 (NOT theta*PI/180: different rounding) */
     md->sec_theta_view[s] = 1.0 / cos(md->theta_view[s]);
-    md->theta_sun[s] = c->theta_w[s] * PI / 180.0;
+    md->theta_sun[s] = c->theta_w[s];
+    md->theta_sun[s] *= PI / 180.0; /* samodel.c:546 */
     md->sec_theta_sun[s] = 1.0 / cos(md->theta_sun[s]);
     for (b = 0; b < c->n_bands[s]; b++) {
       double w = (double)c->wavelengths[s * c->maxb + b];

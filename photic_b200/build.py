@@ -46,5 +46,18 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_host_shim(force: bool = False) -> str:
+    """The C host layer that keeps the reference's samodel() symbol (photic_b200/host/samodel_b200.c)."""
+    src = os.path.join(HERE, "host", "samodel_b200.c")
+    deps = [src, os.path.join(HERE, "host", "photic_abi.h"), os.path.join(HERE, "..", "include", "photic_b200.h")]
+    build()
+    if force or _stale(HOST_SHIM, deps + [LIB]):
+        cmd = ["gcc", "-O2", "-fPIC", "-shared", "-Wall", "-I", os.path.join(HERE, "..", "include"), "-I",
+               os.path.join(HERE, "host"), "-o", HOST_SHIM, src, "-L", CSRC, "-lphotic_b200", "-Wl,-rpath," + CSRC]
+        subprocess.run(cmd, check=True)
+    return HOST_SHIM
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose=True))
+    print(build_host_shim(force="--force" in sys.argv))

@@ -301,7 +301,8 @@ static int invert_device_impl(phb_ctx *c, const phb_scene_desc *desc, const floa
   if (W > 16) W = 16;
   cudaFuncAttributes fa0;
   CK(cudaFuncGetAttributes(&fa0, solve_kernel));
-  const int W_reg = 65536 / (((fa0.numRegs + 7) / 8 * 8) * 32); /* register file: 64K x 32 bit per SM */
+  int W_reg = 65536 / (((fa0.numRegs + 7) / 8 * 8) * 32); /* register file: 64K x 32 bit per SM */
+  if (W_reg > fa0.maxThreadsPerBlock / 32) W_reg = fa0.maxThreadsPerBlock / 32;
   if (W > W_reg) W = W_reg;
   if (const char *e = getenv("PHB_WARPS_PER_CTA")) { int v = atoi(e); if (v >= 1 && v <= W_smem && v <= W_reg) W = v; }
   if (W < 1) W = 1;
@@ -321,8 +322,17 @@ static int invert_device_impl(phb_ctx *c, const phb_scene_desc *desc, const floa
   CK(cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   CK(cudaEventRecord(c->ev[2], st));
   solve_kernel<<<ctas, W * 32, smem, st>>>(sp);
+  {
+    cudaError_t le = cudaGetLastError();
+    if (le != cudaSuccess) {
+      char msg[256];
+      snprintf(msg, sizeof(msg), "solve_kernel launch (ctas=%d W=%d smem=%zu regs=%d maxThreads=%d): %s", ctas, W, smem,
+               fa0.numRegs, fa0.maxThreadsPerBlock, cudaGetErrorString(le));
+      g_last_cuda_error = msg;
+      return PHB_ECUDA;
+    }
+  }
   CK(cudaEventRecord(c->ev[3], st));
-  CK(cudaGetLastError());
 
   if (stats) {
     unsigned long long cnt[4];

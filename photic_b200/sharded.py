@@ -1,0 +1,113 @@
+"""Row-band sharding of one scene over the GPUs of a box (one process per GPU, torch.distributed).
+
+Pixels are independent given a read-only input halo: a pixel reads
+(n_spatial-1)+(n_smoothing_radius-1) rows either side (model/samodel.c:2971-2989,
+model/common.c:240-258), clamped at the image edge. So the data path needs no collective while
+inverting; the only exchanges are
+  * the halo rows between neighbouring bands when every rank holds just its own rows
+    (point-to-point NCCL send/recv over NVLink), and
+  * the final gather of the output planes to rank 0.
+Bands are contiguous and balanced by estimated cost, not by row count: a shallow-water pixel
+(all NBOTTOMS substrates, n = 81..87) costs ~3x a deep one (sand only, n = 45..51).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def halo_rows(n_spatial: int, n_smoothing_radius: int) -> int:
+    nsp = 1 if n_spatial == 0 else n_spatial  # samodel.c:2967
+    return (nsp - 1) + (n_smoothing_radius - 1)
+
+
+def plan_row_bands(row_cost, world: int) -> list[tuple[int, int]]:
+    """Contiguous [r0, r1) per rank with near-equal cumulative cost; every rank gets >= 0 rows."""
+    c = np.asarray(row_cost, dtype=np.float64)
+    nrows = len(c)
+    total = c.sum()
+    if total <= 0:
+        edges = np.linspace(0, nrows, world + 1).round().astype(int)
+    else:
+        cum = np.concatenate([[0.0], np.cumsum(c)])
+        edges = [0]
+        for k in range(1, world):
+            edges.append(int(np.searchsorted(cum, total * k / world, side="left")))
+        edges.append(nrows)
+        edges = np.maximum.accumulate(np.clip(np.array(edges), 0, nrows))
+    return [(int(edges[k]), int(edges[k + 1])) for k in range(world)]
+
+
+def window(r0: int, r1: int, halo: int, nrows: int) -> tuple[int, int, int, int]:
+    """Rows a rank must hold to invert [r0, r1): returns (w0, w1, local_begin, local_end)."""
+    w0, w1 = max(0, r0 - halo), min(nrows, r1 + halo)
+    return w0, w1, r0 - w0, r1 - w0
+
+
+def row_cost(valid: torch.Tensor, shallow: torch.Tensor, shallow_weight: float = 3.0) -> torch.Tensor:
+    """Estimated work per row from the validity and shallow-class masks ([rows, cols] bool)."""
+    v = valid.to(torch.float32)
+    return (v * (1.0 + (shallow_weight - 1.0) * shallow.to(torch.float32))).sum(dim=1)
+
+
+def exchange_halo(band: torch.Tensor, plan, halo: int, rank: int, world: int, group=None) -> torch.Tensor:
+    """band: [planes, r1-r0, cols] rows owned by this rank. Returns the band with up to `halo` rows of the
+    neighbouring bands attached above and below (fewer at the image edge). Empty bands are skipped over."""
+    if halo == 0 or world == 1:
+        return band
+    nrows = plan[-1][1]
+    r0, r1 = plan[rank]
+    if r1 <= r0:
+        return band
+    w0, w1, _, _ = window(r0, r1, halo, nrows)
+    ops, recv = [], {}
+    # rows [w0, r0) come from lower ranks, rows [r1, w1) from higher ranks; symmetric sends.
+    for other in range(world):
+        if other == rank:
+            continue
+        o0, o1 = plan[other]
+        if o1 <= o0:
+            continue
+        ow0, ow1, _, _ = window(o0, o1, halo, nrows)
+        # what I need from `other`
+        lo, hi = max(w0, o0), min(w1, o1)
+        need = [(a, b) for a, b in ((lo, min(hi, r0)), (max(lo, r1), hi)) if b > a]
+        for a, b in need:
+            buf = torch.empty((band.shape[0], b - a, band.shape[2]), dtype=band.dtype, device=band.device)
+            recv[(a, b)] = buf
+            ops.append(dist.P2POp(dist.irecv, buf, other, group))
+        # what `other` needs from me
+        lo, hi = max(ow0, r0), min(ow1, r1)
+        give = [(a, b) for a, b in ((lo, min(hi, o0)), (max(lo, o1), hi)) if b > a]
+        for a, b in give:
+            ops.append(dist.P2POp(dist.isend, band[:, a - r0:b - r0].contiguous(), other, group))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    top = [recv[k] for k in sorted(recv) if k[1] <= r0]
+    bot = [recv[k] for k in sorted(recv) if k[0] >= r1]
+    return torch.cat(top + [band] + bot, dim=1).contiguous()
+
+
+def gather_bands(local: torch.Tensor, plan, rank: int, world: int, dst: int = 0, group=None):
+    """local: [..., r1-r0, cols] rows owned by this rank -> full [..., nrows, cols] on rank dst (None elsewhere).
+    Bands differ in height, so they are padded to the tallest band for one all_gather."""
+    if world == 1:
+        return local
+    hmax = max(b - a for a, b in plan)
+    lead, cols = local.shape[:-2], local.shape[-1]
+    pad = torch.zeros((*lead, hmax, cols), dtype=local.dtype, device=local.device)
+    pad[..., : local.shape[-2], :] = local
+    parts = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(parts, pad, group=group)
+    if rank != dst:
+        return None
+    return torch.cat([parts[k][..., : plan[k][1] - plan[k][0], :] for k in range(world)], dim=-2)
+
+
+def allreduce_minmax(lo: float, hi: float, device, group=None) -> tuple[float, float]:
+    """REFINE without CLIP needs the grid's global min/max (model/refine.c:215-225)."""
+    t = torch.tensor([lo, -hi], dtype=torch.float32, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+    return float(t[0]), float(-t[1])

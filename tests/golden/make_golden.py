@@ -1,0 +1,114 @@
+#!/usr/bin/env python3
+"""Generates tests/golden/*.npz from the UNMODIFIED reference (oracle/_ref/libphotic_ref.so).
+
+Run in the build container (where /root/reference exists):
+    python tests/golden/make_golden.py
+The reference ships no tests or fixtures for this path, so these known
+answers -- produced by the reference's own compiled functions on seeded inputs -- are the pin for
+oracle/photic_oracle.c (tests/test_oracle_vs_golden.py) and, through it, for the CUDA path.
+"""
+import os
+import sys
+from dataclasses import replace
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle.binding import Oracle, SceneCfg, build  # noqa: E402
+from photic_b200 import scene  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+# (file, base config, rows, cols, overrides, use prior)
+SCENES = [
+    ("scene_murion", "murion", 24, 20, {}, True),
+    ("scene_exmouth", "exmouth", 20, 16, {}, True),
+    ("scene_qatar", "qatar", 16, 16, {}, True),
+    ("scene_noprior", "murion", 8, 8, {}, False),
+    ("scene_nspatial1", "murion", 12, 10, {"n_spatial": 1}, True),
+    ("scene_nsmooth2_nb2", "murion", 12, 10, {"n_smoothing_radius": 2, "n_bottoms": 2}, True),
+    ("scene_nspatial3", "murion", 8, 8, {"n_spatial": 3, "n_dates": 2}, True),
+]
+
+
+def main():
+    build()
+    ref = Oracle("reference")
+    rng = np.random.default_rng(20261017)
+    for fname, base, R, Cc, over, use_prior in SCENES:
+        spec = replace(scene.CONFIGS[base].scaled(R, Cc), **over)
+        planes, prior = scene.generate(spec)
+        planes, prior = planes.numpy(), prior.numpy()
+        if fname == "scene_murion":  # edge cases: negative neighbour, prior nodata on a valid pixel, very shallow prior
+            v = np.argwhere(scene.valid_mask(scene.generate(spec)[0]).numpy())
+            planes[1, v[5][0], v[5][1]] = -1.0e-4
+            prior[v[9][0], v[9][1]] = scene.NODATA
+            prior[v[11][0], v[11][1]] = -0.4
+        cfg = SceneCfg.from_spec(spec)
+        ii, jj = np.meshgrid(np.arange(R), np.arange(Cc), indexing="ij")
+        ii, jj = ii.ravel(), jj.ravel()
+        out = ref.invert_pixels(cfg, planes, scene.NODATA, prior if use_prior else None, scene.NODATA, ii, jj, nthreads=8)
+        np.savez_compressed(
+            os.path.join(HERE, fname + ".npz"), planes=planes, prior=prior, use_prior=use_prior,
+            wavelengths=np.array(spec.wavelengths), theta_view=spec.theta_view,
+            theta_sun=np.array([spec.theta_sun(s) for s in range(spec.n_dates)]),
+            h_tide=np.array([spec.h_tide(s) for s in range(spec.n_dates)]), n_smooth=spec.n_smoothing_radius,
+            n_spatial=spec.n_spatial, n_bottoms=spec.n_bottoms, nodata=scene.NODATA, rec=out["rec"],
+            status=out["status"], converged=out["converged"], n_evals=out["n_evals"])
+        print(fname, "valid", int(out["status"].sum()), "of", R * Cc, "conv", int(out["converged"].sum()),
+              "evals", out["n_evals"][out["status"] == 1].mean())
+
+    # known answers of the objective / forward model on random parameter vectors
+    kat = {}
+    for tag, ns, nb, nr in (("a", 4, 3, 9), ("b", 6, 1, 9), ("c", 8, 3, 6), ("d", 2, 2, 4)):
+        spec = replace(scene.CONFIGS["murion"], n_dates=ns)
+        cfg = SceneCfg.from_spec(spec)
+        meas = rng.uniform(0.002, 0.02, (nr, ns, 4))
+        n = nr + 2 * nr * nb + 3 * ns
+        params = np.concatenate([rng.uniform(0.3, 45, (64, nr)), rng.uniform(5, 60, (64, nr * nb)),
+                                 rng.uniform(0.1, 2, (64, nr * nb)), rng.uniform(0.5, 12, (64, 3 * ns))], axis=1)
+        params[::7] *= -1.0  # sign is ignored through fabs
+        params[3, :nr] = 0.7  # shallow: K penalties
+        params[4, :nr] = 1.7
+        params[5, :nr] = 2.7
+        params[6, :nr] = 3.7
+        params[8, :nr] = 4.7
+        assert params.shape[1] == n
+        origin = nr // 2
+        out, rrs, K = ref.error_kat(cfg, nb, nr, origin, meas, params)
+        for k, v in (("meas", meas), ("params", params), ("out", out), ("rrs", rrs), ("K", K),
+                     ("meta", np.array([ns, nb, nr, origin]))):
+            kat[f"{tag}_{k}"] = v
+    np.savez_compressed(os.path.join(HERE, "kat_objective.npz"), **kat)
+
+    # nelmin known answers on analytic functions (incl. ties, restarts, kcount exhaustion)
+    nm = {}
+    idx = 0
+    for fn_id in (0, 1, 2):
+        for n in (2, 5, 12, 30):
+            for kcount in (5000, 300):
+                start = rng.uniform(-2, 3, n)
+                step = rng.uniform(0.3, 2.0, n)
+                xmin, y, ic, nr_, ifl = ref.nelmin_kat(fn_id, start, step, 1e-2, 100 if n > 5 else 10, kcount)
+                nm[f"{idx}_in"] = np.concatenate([[fn_id, n, kcount, 100 if n > 5 else 10], start, step])
+                nm[f"{idx}_out"] = np.concatenate([[y, ic, nr_, ifl], xmin])
+                idx += 1
+    np.savez_compressed(os.path.join(HERE, "kat_nelmin.npz"), **nm)
+
+    # interp_1d / approx_equal / band tables
+    X = np.array([443.0, 482.0, 561.0, 655.0])
+    Y = rng.uniform(0.001, 0.02, 4)
+    xs = np.array([440.0, 443.0, 443.001, 482.0, 490.0, 550.0, 561.0, 640.0, 655.0, 654.999, 750.0, 400.0])
+    vals = np.array([ref.interp_1d(X, Y, x) for x in xs])
+    ae = np.array([[a, b, e, ref.approx_equal(a, b, e)] for a, b, e in
+                   [(-9999.0, -9999.0, 1e-6), (-9999.0, -9998.99, 1e-6), (-9999.0, -9998.0, 1e-4), (0.0, 0.0, 1e-6),
+                    (1e-7, 0.0, 1e-6), (0.01, 0.0100000001, 1e-6), (443.0, 443.004, 1e-5), (443.0, 443.005, 1e-5)]])
+    cfg = SceneCfg.from_spec(scene.CONFIGS["abudhabi"])
+    t0, t1 = ref.tables(cfg)
+    np.savez_compressed(os.path.join(HERE, "kat_misc.npz"), X=X, Y=Y, xs=xs, vals=vals, approx=ae, tables=t0, aux=t1)
+    print("done")
+
+
+if __name__ == "__main__":
+    main()

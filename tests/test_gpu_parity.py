@@ -1,0 +1,201 @@
+"""Parity tests proper: the CUDA path (through the C ABI) against the CPU oracle and the committed
+golden vectors of the reference. The bar is BIT equality of every retrieved parameter in double
+precision, identical evaluation counts and identical convergence flags; that implies the stated
+tolerance (|dH| <= 1e-3 m, relative <= 1e-4 on the other parameters for >= 99.9 % of pixels)."""
+from dataclasses import replace
+
+import numpy as np
+import pytest
+
+from conftest import SCENE_FIXTURES, bits_equal, cfg_from_golden, desc_from_golden, load_golden
+
+pytestmark = pytest.mark.gpu
+
+H_TOL, REL_TOL = 1.0e-3, 1.0e-4  # north_star tolerance, for the float32 output planes
+
+
+def _full_grid(R, C):
+    ii, jj = np.meshgrid(np.arange(R), np.arange(C), indexing="ij")
+    return ii.ravel(), jj.ravel()
+
+
+def _check_planes_against_records(out, rec, pix, ncols, ns):
+    """The float32 planes the shim hands back are the float casts of the records (samodel.c:1120-1160)."""
+    i, j = pix // ncols, pix % ncols
+    assert np.array_equal(out["depth"][i, j], -(rec[:, 0].astype(np.float32)))
+    for col, name in ((1, "model_error"), (2, "bottom_albedo"), (3, "bottom_sand"), (4, "bottom_seagrass"),
+                      (5, "bottom_coral"), (6, "K_min"), (7, "index_optical_depth"), (8, "bottom_type")):
+        assert np.array_equal(out[name][i, j], rec[:, col].astype(np.float32)), name
+    K = rec[:, 16:16 + ns * 4].reshape(-1, ns, 4).astype(np.float32)
+    assert np.array_equal(out["K"][:, :, i, j].transpose(2, 0, 1), K)
+    pgx = rec[:, 16 + ns * 4:16 + ns * 4 + 3 * ns].reshape(-1, ns, 3).astype(np.float32)
+    for k, name in enumerate("PGX"):
+        assert np.array_equal(out[name][:, i, j].T, pgx[:, :, k]), name
+
+
+@pytest.mark.parametrize("name", SCENE_FIXTURES)
+def test_golden_scenes_bit_exact(inverter, name):
+    """Committed outputs of the UNMODIFIED reference (tests/golden/make_golden.py)."""
+    g = load_golden(name)
+    desc = desc_from_golden(g)
+    _, R, C = g["planes"].shape
+    prior = g["prior"] if bool(g["use_prior"]) else None
+    out, st = inverter.invert_host(desc, g["planes"], prior, debug=True)
+    ok = g["status"] == 1
+    pix = np.nonzero(ok)[0]
+    assert st["n_valid"] == ok.sum() and np.array_equal(out["pix"], pix)
+    assert np.array_equal(out["rec_evals"], g["n_evals"][ok])
+    assert np.array_equal(out["rec_converged"], g["converged"][ok])
+    assert bits_equal(out["rec"], g["rec"][ok]).all()
+    ns = len(g["theta_sun"])
+    _check_planes_against_records(out, out["rec"], pix, C, ns)
+    # identical convergence-flag map, defaults where nothing is inverted (samodel.c:819-829)
+    assert np.array_equal(out["converged"].ravel(), g["converged"].astype(np.uint8))
+    assert np.array_equal(out["n_evals"].ravel(), g["n_evals"])
+    bad = ~ok.reshape(R, C)
+    assert (out["bottom_sand"][bad] == -9999.0).all() and (out["bottom_type"][bad] == -9999.0).all()
+    assert (out["depth"][bad] == 0.0).all() and (out["K_min"][bad] == 0.0).all()
+
+
+@pytest.mark.parametrize("cfg_name,R,C,over", [
+    ("murion", 40, 31, {}), ("exmouth", 37, 29, {}), ("abudhabi", 24, 20, {}), ("qatar", 30, 30, {}),
+    ("pilbara", 16, 33, {}), ("murion", 1, 23, {}), ("murion", 19, 1, {}), ("murion", 12, 12, {"n_spatial": 0}),
+    ("exmouth", 12, 12, {"n_bottoms": 1}), ("murion", 10, 10, {"n_dates": 1}), ("murion", 10, 10, {"n_bottoms": 8}),
+])
+def test_seeded_scenes_vs_oracle(inverter, oracle_port, cfg_name, R, C, over):
+    """Fresh seeded scenes (ragged shapes, single row / column, 1 date, 1 and 8 substrates, NSPATIAL 0)."""
+    from oracle.binding import SceneCfg
+    from photic_b200 import capi, scene
+    spec = replace(scene.CONFIGS[cfg_name].scaled(R, C), **over)
+    planes, prior = scene.generate(spec)
+    planes, prior = planes.numpy(), prior.numpy()
+    out, st = inverter.invert_host(capi.desc_from_spec(spec), planes, prior, debug=True)
+    ii, jj = _full_grid(R, C)
+    ref = oracle_port.invert_pixels(SceneCfg.from_spec(spec), planes, scene.NODATA, prior, scene.NODATA, ii, jj)
+    ok = ref["status"] == 1
+    assert ok.sum() > 0 and st["n_valid"] == ok.sum()
+    assert np.array_equal(out["pix"], np.nonzero(ok)[0])
+    assert np.array_equal(out["rec_evals"], ref["n_evals"][ok]) and np.array_equal(out["rec_converged"], ref["converged"][ok])
+    assert bits_equal(out["rec"], ref["rec"][ok]).all()
+    assert st["n_evals"] >= ref["n_evals"].sum() and st["n_converged"] == ref["converged"].sum()
+    # the stated tolerance on the float32 planes, spelled out (implied by bit equality above)
+    d = -out["depth"].ravel()[ok]
+    assert (np.abs(d - ref["rec"][ok, 0]) <= H_TOL).mean() >= 0.999
+    k = out["K_min"].ravel()[ok]
+    assert (np.abs(k - ref["rec"][ok, 6]) <= REL_TOL * np.abs(ref["rec"][ok, 6]) + 1e-12).mean() >= 0.999
+
+
+def test_empty_and_all_land_scenes(inverter):
+    from photic_b200 import capi, scene
+    spec = scene.CONFIGS["murion"].scaled(9, 7)
+    planes = np.full((spec.n_planes, 9, 7), scene.NODATA, dtype=np.float32)
+    prior = np.full((9, 7), scene.NODATA, dtype=np.float32)
+    out, st = inverter.invert_host(capi.desc_from_spec(spec), planes, prior)
+    assert st["n_valid"] == 0 and (out["bottom_sand"] == -9999.0).all() and (out["depth"] == 0.0).all()
+    planes[:] = -0.5  # negative reflectance everywhere: valid nowhere (samodel.c:939)
+    out, st = inverter.invert_host(capi.desc_from_spec(spec), planes, prior)
+    assert st["n_valid"] == 0
+
+
+def test_row_band_shards_equal_whole_scene(inverter):
+    """Size-independent property used at full scale: inverting row bands with their halo rows gives
+    exactly the unsharded planes (edge clamping happens at the global edge only)."""
+    from photic_b200 import capi, scene, sharded
+    spec = scene.CONFIGS["abudhabi"].scaled(30, 22)
+    planes, prior = scene.generate(spec)
+    planes, prior = planes.numpy(), prior.numpy()
+    whole, _ = inverter.invert_host(capi.desc_from_spec(spec), planes, prior)
+    halo = sharded.halo_rows(spec.n_spatial, spec.n_smoothing_radius)
+    cost = scene.valid_mask(__import__("torch").from_numpy(planes)).sum(dim=1).numpy()
+    for world in (2, 4):
+        plan = sharded.plan_row_bands(cost, world)
+        for r0, r1 in plan:
+            if r1 <= r0:
+                continue
+            w0, w1, lb, le = sharded.window(r0, r1, halo, spec.nrows)
+            part, _ = inverter.invert_host(capi.desc_from_spec(spec, nrows=w1 - w0), np.ascontiguousarray(planes[:, w0:w1]),
+                                           np.ascontiguousarray(prior[w0:w1]), row_begin=lb, row_end=le)
+            for name in ("depth", "K_min", "bottom_albedo", "index_optical_depth", "converged", "n_evals", "P", "K"):
+                a = part[name][..., lb:le, :]
+                b = whole[name][..., r0:r1, :]
+                assert np.array_equal(a, b), (name, world, r0, r1)
+
+
+def test_run_to_run_determinism_and_device_entry(inverter):
+    """Queue order is nondeterministic (atomics); results must not be. Also exercises phb_invert_device."""
+    import torch
+    from photic_b200 import capi, scene
+    from photic_b200.samodel import Inverter
+    spec = scene.CONFIGS["qatar"].scaled(48, 40)
+    planes, prior = scene.generate(spec, device="cuda")
+    desc = capi.desc_from_spec(spec)
+    outs = []
+    for _ in range(2):
+        o = Inverter.alloc_device_outputs(desc, "cuda")
+        st = inverter.invert_device(desc, planes, prior, o)
+        torch.cuda.synchronize()
+        outs.append({k: v.cpu().numpy() for k, v in o.items()})
+    for k in outs[0]:
+        assert np.array_equal(outs[0][k], outs[1][k]), k
+    host, st_h = inverter.invert_host(desc, planes.cpu().numpy(), prior.cpu().numpy())
+    for k in outs[0]:
+        assert np.array_equal(outs[0][k], host[k]), k
+    assert st["n_valid"] == st_h["n_valid"] > 0 and st["alg_flops"] == st_h["alg_flops"] > 0
+
+
+def test_objective_known_answers_on_device(inverter):
+    """samodel_error / samodel_Rrs on random parameter vectors: reference's own outputs (golden)."""
+    from photic_b200 import capi, scene
+    k = load_golden("kat_objective")
+    for tag in "abcd":
+        ns, nb, nr, origin = (int(v) for v in k[f"{tag}_meta"])
+        spec = replace(scene.CONFIGS["murion"], n_dates=ns)
+        got = inverter.kat_objective(capi.desc_from_spec(spec), nb, nr, origin, k[f"{tag}_meas"], k[f"{tag}_params"])
+        assert bits_equal(got, k[f"{tag}_out"]).all(), tag
+
+
+def test_device_math_equals_host_libm(inverter):
+    """exp/log/pow on the device == the libm the reference links (same process, math module / numpy ufunc free)."""
+    import math
+    rng = np.random.default_rng(5)
+    n = 100_000
+    x = np.concatenate([rng.uniform(-760, 30, n), [0.0, -0.0, -745.2, 709.0, np.inf, -np.inf]])
+    ref = np.array([math.exp(v) if v < 709.7 else np.inf for v in x])
+    assert bits_equal(inverter.kat_math(0, x), ref).all()
+    x = np.exp(rng.uniform(-40, 10, n))
+    assert bits_equal(inverter.kat_math(1, x), np.array([math.log(v) for v in x])).all()
+    x, y = rng.uniform(0.3, 1.5, n), rng.uniform(-3, 3, n)
+    assert bits_equal(inverter.kat_math(2, x, y), np.array([math.pow(a, b) for a, b in zip(x, y)])).all()
+
+
+def test_refine_matches_oracle(inverter, oracle_port):
+    """REFINE (model/refine.c): every flag combination against the CPU restatement, bit exact."""
+    from photic_b200 import capi
+    rng = np.random.default_rng(11)
+    grid = (-rng.uniform(0.2, 35.0, (57, 43))).astype(np.float32)
+    grid[rng.uniform(size=grid.shape) < 0.2] = -9999.0
+    land = np.where(rng.uniform(size=grid.shape) < 0.3, -9999.0, 1.0).astype(np.float32)
+    shallow = np.where(rng.uniform(size=grid.shape) < 0.2, -9999.0, 1.0).astype(np.float32)
+    args = np.array([-30.0, -0.5, -40.0, 0.0, 1.3, 0.9, -0.25, -32.0, -1.0, 1.1, 0.95], dtype=np.float32)
+    for flags in (0, 1, 2, 3, 4, 8, 16, 1 | 2 | 4 | 8 | 16, 2 | 16, 1 | 8):
+        for masks in ((None, None), (land, shallow)):
+            a2 = args.copy()
+            if flags == 3:
+                a2[4] = 1.0  # SHAPE 1.0: the linear rescale branch
+            got = inverter.refine_host(grid, -9999.0, flags, a2, land=masks[0], shallow=masks[1])
+            exp = oracle_port.refine(grid, -9999.0, masks[0], -9999.0, masks[1], -9999.0, flags, a2)
+            assert np.array_equal(got.view(np.int32), exp.view(np.int32)), (flags, masks[0] is not None)
+
+
+def test_python_samodel_surface(inverter):
+    """The reference-named call (scene / geogrid / samodel) fills the caller's grids in place."""
+    from photic_b200 import scene as sc
+    from photic_b200.samodel import geogrid, samodel, scene
+    spec = sc.CONFIGS["murion"].scaled(16, 12)
+    planes, prior = sc.generate(spec)
+    grids = [geogrid(planes[g].numpy().copy()) for g in range(spec.n_planes)] + [geogrid(prior.numpy().copy())]
+    scenes = [scene(f"d{s}", [4 * s + b for b in range(4)], list(spec.wavelengths), spec.theta_view, spec.theta_sun(s),
+                    spec.h_tide(s)) for s in range(spec.n_dates)]
+    outs = [np.zeros((16, 12), dtype=np.float32) for _ in range(10)]
+    st = samodel(scenes, grids, list(range(spec.n_dates)), spec.n_dates, True, grids[-1], 1, 2, 3, *outs, inverter=inverter)
+    assert st["n_valid"] > 0 and (outs[0] <= 0).all() and (outs[0] < 0).sum() == st["n_valid"]

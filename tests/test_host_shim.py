@@ -1,0 +1,119 @@
+"""The C host layer (photic_b200/host/samodel_b200.c) that keeps the reference's samodel() symbol."""
+import ctypes as C
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+REF = "/root/reference/model"
+
+
+class Geogrid(C.Structure):  # photic_abi.h / model/common.h:69-84
+    _fields_ = [("nrows", C.c_int), ("ncols", C.c_int), ("cellsize", C.c_float), ("wlon", C.c_float),
+                ("slat", C.c_float), ("elon", C.c_float), ("nlat", C.c_float), ("nodata_value", C.c_float),
+                ("lambda_", C.c_float), ("theta_v", C.c_float), ("theta_w", C.c_float),
+                ("array", C.POINTER(C.POINTER(C.c_float)))]
+
+
+class Scene(C.Structure):  # photic_abi.h / model/common.h:194-218
+    _fields_ = [("scene_name", C.c_char * 2048), ("n_bands", C.c_int), ("nrows", C.c_int), ("ncols", C.c_int),
+                ("band_indexes", C.c_int * 265), ("wavelengths", C.c_int * 265), ("theta_w", C.c_double),
+                ("theta_v", C.c_double), ("H_tide", C.c_double), ("R_inf", C.c_double * 265),
+                ("R_sigma", C.c_double * 265), ("K", C.c_double * 265), ("K_sigma", C.c_double * 265),
+                ("ratio_min", C.c_double), ("ratio_max", C.c_double), ("slope_min", C.c_double),
+                ("slope_max", C.c_double), ("pgx_present", C.c_int), ("ps_p", C.c_int), ("ps_g", C.c_int),
+                ("ps_x", C.c_int)]
+
+
+PROBE = r'''
+#include <stdio.h>
+#include <stddef.h>
+%s
+int main(void) {
+  printf("%%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu\n", sizeof(GEO), offsetof(GEO, array), offsetof(GEO, nodata_value),
+         sizeof(SCN), offsetof(SCN, band_indexes), offsetof(SCN, wavelengths), offsetof(SCN, theta_w), offsetof(SCN, H_tide));
+  return 0;
+}
+'''
+
+
+def _probe(header_block, flags):
+    with tempfile.TemporaryDirectory() as td:
+        src, exe = os.path.join(td, "p.c"), os.path.join(td, "p")
+        open(src, "w").write(PROBE % header_block)
+        subprocess.run(["gcc", "-w", *flags, src, "-o", exe], check=True)
+        return [int(v) for v in subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()]
+
+
+def test_abi_mirror_matches_ctypes():
+    mine = _probe('#include "photic_abi.h"\n#define GEO photic_geogrid\n#define SCN photic_scene',
+                  ["-I", os.path.join(ROOT, "photic_b200", "host")])
+    assert mine[0] == C.sizeof(Geogrid) and mine[3] == C.sizeof(Scene)
+    assert mine[1] == Geogrid.array.offset and mine[4] == Scene.band_indexes.offset and mine[7] == Scene.H_tide.offset
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference headers absent")
+def test_abi_mirror_matches_reference_headers():
+    mine = _probe('#include "photic_abi.h"\n#define GEO photic_geogrid\n#define SCN photic_scene',
+                  ["-I", os.path.join(ROOT, "photic_b200", "host")])
+    ref = _probe('#include "common.h"\n#define GEO geogrid\n#define SCN scene', ["-fcommon", "-I", REF])
+    assert mine == ref
+
+
+def test_shim_exports_reference_symbol(product_lib):
+    from photic_b200 import build
+    so = build.build_host_shim()
+    lib = C.CDLL(so)
+    assert hasattr(lib, "samodel")
+
+
+@pytest.mark.gpu
+def test_shim_samodel_equals_library(inverter):
+    """Call the C samodel() the way bam.c:3236 does (row-pointer grids, geogrid by value)."""
+    from photic_b200 import build, capi, scene
+    lib = C.CDLL(build.build_host_shim())
+    spec = scene.CONFIGS["murion"].scaled(18, 14)
+    planes, prior = scene.generate(spec)
+    planes, prior = planes.numpy(), prior.numpy()
+    R, Cc, ns = spec.nrows, spec.ncols, spec.n_dates
+    keep = []
+
+    def rows(a):
+        a = np.ascontiguousarray(a, dtype=np.float32)
+        ptrs = (C.POINTER(C.c_float) * R)(*[a[r].ctypes.data_as(C.POINTER(C.c_float)) for r in range(R)])
+        keep.extend([a, ptrs])
+        return ptrs, a
+
+    grids = (Geogrid * (spec.n_planes + 1))()
+    for g in range(spec.n_planes + 1):
+        p, _ = rows(planes[g] if g < spec.n_planes else prior)
+        grids[g].nrows, grids[g].ncols, grids[g].nodata_value, grids[g].cellsize = R, Cc, scene.NODATA, 30.0
+        grids[g].array = C.cast(p, C.POINTER(C.POINTER(C.c_float)))
+    scenes = (Scene * ns)()
+    for s in range(ns):
+        scenes[s].scene_name = f"date{s}".encode()
+        scenes[s].n_bands, scenes[s].nrows, scenes[s].ncols = 4, R, Cc
+        for b in range(4):
+            scenes[s].band_indexes[b] = 4 * s + b
+            scenes[s].wavelengths[b] = spec.wavelengths[b]
+        scenes[s].theta_v, scenes[s].theta_w, scenes[s].H_tide = spec.theta_view, spec.theta_sun(s), spec.h_tide(s)
+    idx = (C.c_int * ns)(*range(ns))
+    outs = [rows(np.full((R, Cc), 7.0, dtype=np.float32)) for _ in range(10)]
+    lib.samodel.restype = None
+    lib.samodel.argtypes = [C.POINTER(Scene), C.POINTER(Geogrid), C.POINTER(C.c_int), C.c_int, C.c_int, Geogrid, C.c_int,
+                            C.c_int, C.c_int] + [C.POINTER(C.POINTER(C.c_float))] * 10 + [C.c_float, C.c_int, C.c_int]
+    lib.samodel(scenes, grids, idx, ns, 1, grids[spec.n_planes], 1, 2, 3, *[o[0] for o in outs], 8.0, 0, 1)
+    exp, st = inverter.invert_host(capi.desc_from_spec(spec), planes, prior)
+    order = ["depth", None, "model_error", "bottom_albedo", "bottom_sand", "bottom_seagrass", "bottom_coral", "K_min",
+             "bottom_type", "index_optical_depth"]
+    for k, name in enumerate(order):
+        got = outs[k][1]
+        if name is None:
+            assert (got == 0.0).all()   # depth_sigma
+        else:
+            assert np.array_equal(got.view(np.int32), exp[name].view(np.int32)), name
+    assert st["n_valid"] > 50
