@@ -15,26 +15,27 @@ __global__ void kat_objective_kernel(const SolveParams p, int nb_active, int n_r
   stage_cta(p, M, phb_smem);
   __syncthreads();
   Warp w;
+  const int lane = threadIdx.x & 31, SB = p.L.SB, Ns = p.L.Ns;
   bind_warp(w, p, phb_smem, 0, 0);
-  w.max_bands = M.max_bands;
-  w.Nr = n_regions; w.Nb = nb_active; w.origin = origin;
-  w.n = n_regions + 2 * n_regions * nb_active + 3 * w.Ns;
-  w.T = n_regions * w.SB;
-  for (int t = w.lane; t < w.T; t += 32) w.meas[t] = meas[t];
+  Pixel px;
+  px.Nr = n_regions; px.Nb = nb_active; px.origin = origin;
+  size_pixel(px, lane, SB, Ns, p.L.simplex_doubles);
+  for (int t = lane; t < px.T; t += 32) w.meas[t] = meas[t];
   __syncwarp();
   phm::Tables tb;
-  tb.exp_tab = reinterpret_cast<const uint64_t *>(w.exp_tab);
+  tb.exp_tab = w.exp_tab;
   tb.log_tab = p.log_tab;
   tb.pow_tab = p.pow_tab;
   double Bs, Ps, Xs;
-  derive_pixel_constants(w, M, tb, Bs, Ps, Xs);
+  derive_pixel_constants(w, px, M, tb, lane, SB, Ns, Bs, Ps, Xs);
+  Side side;
   for (int v = 0; v < nvec; v++) {
-    for (int i = w.lane; i < w.n; i += 32) w.xmin[i] = params[(size_t)v * w.n + i];
+    for (int i = lane; i < px.n; i += 32) w.xmin[i] = params[(size_t)v * px.n + i];
     __syncwarp();
-    const double e = objective(w, w.xmin, true);
-    if (w.lane == 0) {
+    const double e = objective(w, px, lane, SB, Ns, w.xmin, true, side);
+    if (lane == 0) {
       double *o = out6 + (size_t)v * 6;
-      o[0] = e; o[1] = w.e_rrs; o[2] = w.e_depth; o[3] = w.e_bottom; o[4] = w.e_K; o[5] = w.bottom_albedo;
+      o[0] = e; o[1] = side.e_rrs; o[2] = side.e_depth; o[3] = side.e_bottom; o[4] = side.e_K; o[5] = side.bottom_albedo;
     }
     __syncwarp();
   }

@@ -293,20 +293,25 @@ static int invert_device_impl(phb_ctx *c, const phb_scene_desc *desc, const floa
   const int NrMax = (2 * nsp - 1) * (2 * nsp - 1);
   SolveParams sp;
   sp.L = make_layout(M.SB, M.n_scenes, M.n_bottoms, NrMax);
-  const long long slab_doubles = (long long)(sp.L.nmax + 1) * sp.L.nmax + sp.L.nmax + sp.L.Tmax;
-  int W_smem = (int)(((long long)c->smem_optin - sp.L.cta_bytes) / sp.L.warp_bytes);
-  /* keep the simplex slabs of all resident warps inside ~3/4 of L2 (they are re-read every iteration) */
-  int W_l2 = (int)((c->l2_bytes * 3 / 4) / ((size_t)c->n_sm * slab_doubles * 8));
-  int W = W_smem < W_l2 ? W_smem : W_l2;
-  if (W > 16) W = 16;
+  const long long simplex_doubles = (long long)(sp.L.nmax + 1) * sp.L.nmax;
+  const long long slab_doubles = simplex_doubles + sp.L.nmax + sp.L.Tmax;
   cudaFuncAttributes fa0;
   CK(cudaFuncGetAttributes(&fa0, solve_kernel));
-  int W_reg = 65536 / (((fa0.numRegs + 7) / 8 * 8) * 32); /* register file: 64K x 32 bit per SM */
-  if (W_reg > fa0.maxThreadsPerBlock / 32) W_reg = fa0.maxThreadsPerBlock / 32;
-  if (W > W_reg) W = W_reg;
-  if (const char *e = getenv("PHB_WARPS_PER_CTA")) { int v = atoi(e); if (v >= 1 && v <= W_smem && v <= W_reg) W = v; }
-  if (W < 1) W = 1;
+  const int W_reg = fa0.maxThreadsPerBlock / 32;
+  const int W_smem = (int)(((long long)c->smem_optin - sp.L.cta_bytes) / sp.L.warp_bytes);
   if (W_smem < 1) return PHB_EINVAL; /* configuration does not fit shared memory */
+  /* Occupancy vs simplex residency: each warp's leftover shared memory holds the first rows of its
+   * simplex (all of it for sand-only pixels); the rest lives in an L2-resident global slab. Default:
+   * 16 warps (4 per scheduler) when they fit; PHB_WARPS_PER_CTA overrides (tuning / profiling). */
+  int W = 16;
+  if (const char *e = getenv("PHB_WARPS_PER_CTA")) { int v = atoi(e); if (v >= 1) W = v; }
+  if (W > W_reg) W = W_reg;
+  if (W > W_smem) W = W_smem;
+  if (W < 1) W = 1;
+  long long cache_bytes = ((long long)c->smem_optin - sp.L.cta_bytes) / W - sp.L.warp_bytes;
+  if (cache_bytes > simplex_doubles * 8) cache_bytes = simplex_doubles * 8;
+  if (const char *e = getenv("PHB_SIMPLEX_SMEM_BYTES")) { long long v = atoll(e); if (v >= 0 && v < cache_bytes) cache_bytes = v; }
+  add_simplex_cache(sp.L, (int)cache_bytes);
   int ctas = c->n_sm;
   if (const char *e = getenv("PHB_CTAS")) { int v = atoi(e); if (v >= 1) ctas = v; }
   const size_t smem = (size_t)sp.L.cta_bytes + (size_t)W * sp.L.warp_bytes;
