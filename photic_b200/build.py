@@ -29,6 +29,26 @@ def _stale(target: str, sources: list[str]) -> bool:
     return any(os.path.getmtime(s) > t for s in sources)
 
 
+def build_variant(tag: str, defines: list[str]) -> str:
+    """Experimental build with extra -D flags -> csrc/libphotic_b200_<tag>.so (select with PHB_LIB=<path>)."""
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    out = os.path.join(CSRC, f"libphotic_b200_{tag}.so")
+    cmd = [nvcc, *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-o", out, os.path.join(CSRC, "photic_b200.cu")]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    log = r.stdout + r.stderr
+    if r.returncode:
+        print(log, file=sys.stderr)
+        raise RuntimeError("nvcc failed")
+    for line in log.splitlines():
+        if "solve_kernel" in line or "Used" in line and "128" in line or "spill" in line and "solve" in line:
+            pass
+    import re
+    m = re.search(r"solve_kernel.*?\n.*?\n\s*(\d+) bytes stack frame, (\d+) bytes spill stores.*?\n.*?Used (\d+) registers", log, re.S)
+    if m:
+        print(f"{tag}: stack {m.group(1)} spill {m.group(2)} regs {m.group(3)}")
+    return out
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))]
     srcs += [os.path.join(HERE, "..", "include", f) for f in ("photic_b200.h", "photic_spectra.h")]

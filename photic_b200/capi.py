@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "csrc", "libphotic_b200.so")
+LIB_PATH = os.environ.get("PHB_LIB") or os.path.join(HERE, "csrc", "libphotic_b200.so")
 
 MAX_SCENES, MAX_BANDS, MAX_BOTTOMS = 16, 8, 8
 

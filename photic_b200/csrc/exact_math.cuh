@@ -29,8 +29,10 @@
 
 #if defined(__CUDACC__)
 #define PHM_HD __host__ __device__ __forceinline__
+#define PHM_RARE __host__ __device__ __noinline__ /* rare paths: out of the hot instruction stream */
 #else
 #define PHM_HD static inline
+#define PHM_RARE static inline
 #endif
 
 namespace phm {
@@ -103,19 +105,8 @@ PHM_HD double exp_special(double tmp, uint64_t sbits, uint64_t ki, bool signed_s
   return mul_(0x1p-1022, y);
 }
 
-/* __exp_fma (libm.so.6 @0x79b60), e_exp.c */
-PHM_HD double exp(double x, const uint64_t *T) {
-  uint64_t ix = bits(x);
-  uint32_t abstop = (uint32_t)(ix >> 52) & 0x7ff;
-  if (abstop - 0x3c9u >= 0x3fu) {
-    if (abstop - 0x3c9u >= 0x80000000u) return add_(1.0, x); /* |x| < 2^-54 (0 is a common input) */
-    if (abstop >= 0x409u) {                                  /* |x| >= 1024 */
-      if (ix == 0xfff0000000000000ull) return 0.0;
-      if (abstop >= 0x7ffu) return add_(1.0, x);
-      return (ix >> 63) ? 0.0 : from_bits(0x7ff0000000000000ull); /* __math_uflow / __math_oflow */
-    }
-    abstop = 0; /* 512 <= |x| < 1024 */
-  }
+/* the part of __exp_fma after the range checks; abstop == 0 marks 512 <= |x| < 1024 */
+PHM_HD double exp_core(double x, uint32_t abstop, const uint64_t *T) {
   double kd = fma_(x, k::InvLn2N, k::Shift);
   uint64_t ki = bits(kd);
   kd = sub_(kd, k::Shift);
@@ -137,13 +128,31 @@ PHM_HD double exp(double x, const uint64_t *T) {
   return fma_(scale, tmp, scale);
 }
 
+/* |x| < 2^-54 or |x| >= 512: rare, kept out of the hot instruction stream on the device */
+PHM_RARE double exp_rare(double x, const uint64_t *T) {
+  uint64_t ix = bits(x);
+  uint32_t abstop = (uint32_t)(ix >> 52) & 0x7ff;
+  if (abstop - 0x3c9u >= 0x80000000u) return add_(1.0, x); /* |x| < 2^-54 (0 is a common input) */
+  if (abstop >= 0x409u) {                                  /* |x| >= 1024 */
+    if (ix == 0xfff0000000000000ull) return 0.0;
+    if (abstop >= 0x7ffu) return add_(1.0, x);
+    return (ix >> 63) ? 0.0 : from_bits(0x7ff0000000000000ull); /* __math_uflow / __math_oflow */
+  }
+  return exp_core(x, 0, T); /* 512 <= |x| < 1024 */
+}
+
+/* __exp_fma (libm.so.6 @0x79b60), e_exp.c */
+PHM_HD double exp(double x, const uint64_t *T) {
+  uint32_t abstop = (uint32_t)(bits(x) >> 52) & 0x7ff;
+  if (abstop - 0x3c9u >= 0x3fu) return exp_rare(x, T);
+  return exp_core(x, abstop, T);
+}
+
 /* ---- log ------------------------------------------------------------------------------- */
 
-/* __log_fma (libm.so.6 @0x79d50), e_log.c */
-PHM_HD double log(double x, const double *T) {
+/* 1 - 0x1p-4 <= x < 1 + 0x1.09p-4: the dedicated polynomial of e_log.c */
+PHM_RARE double log_near1(double x) {
   uint64_t ix = bits(x);
-  uint32_t top = (uint32_t)(ix >> 48);
-  if (ix - 0x3fee000000000000ull < 0x3090000000000ull) { /* 1 - 0x1p-4 <= x < 1 + 0x1.09p-4 */
     if (ix == 0x3ff0000000000000ull) return 0.0;
     double r = sub_(x, 1.0);
     double p1 = fma_(r, k::LB2, k::LB1);
@@ -167,14 +176,10 @@ PHM_HD double log(double x, const double *T) {
     lo = fma_(mul_(k::LB0, rlo), rs, lo);
     double y = fma_(p, r3, lo);
     return add_(hi, y);
-  }
-  if (top - 0x0010u >= 0x7ff0u - 0x0010u) {
-    if (ix * 2 == 0) return from_bits(0xfff0000000000000ull); /* log(+-0) = -inf */
-    if (ix == 0x7ff0000000000000ull) return x;                /* log(inf) = inf */
-    if ((top & 0x8000u) || (top & 0x7ff0u) == 0x7ff0u) return from_bits(0x7ff8000000000000ull); /* x<0 / nan */
-    ix = bits(mul_(x, 0x1p52)); /* subnormal: normalise */
-    ix -= 52ull << 52;
-  }
+}
+
+/* table path of __log_fma for a positive normal argument given by its bits */
+PHM_HD double log_core(uint64_t ix, const double *T) {
   uint64_t tmp = ix - 0x3fe6000000000000ull;
   uint32_t i = (uint32_t)(tmp >> 45) & 127u;
   int32_t kk = (int32_t)((int64_t)tmp >> 52);
@@ -195,6 +200,27 @@ PHM_HD double log(double x, const double *T) {
   double p = fma_(p34, r2, p12);
   double y = fma_(r3, p, lo);
   return add_(y, hi);
+}
+
+/* zero / negative / inf / nan / subnormal arguments */
+PHM_RARE double log_rare(double x, const double *T) {
+  uint64_t ix = bits(x);
+  uint32_t top = (uint32_t)(ix >> 48);
+  if (ix * 2 == 0) return from_bits(0xfff0000000000000ull); /* log(+-0) = -inf */
+  if (ix == 0x7ff0000000000000ull) return x;                /* log(inf) = inf */
+  if ((top & 0x8000u) || (top & 0x7ff0u) == 0x7ff0u) return from_bits(0x7ff8000000000000ull); /* x<0 / nan */
+  ix = bits(mul_(x, 0x1p52)); /* subnormal: normalise */
+  ix -= 52ull << 52;
+  return log_core(ix, T);
+}
+
+/* __log_fma (libm.so.6 @0x79d50), e_log.c */
+PHM_HD double log(double x, const double *T) {
+  uint64_t ix = bits(x);
+  uint32_t top = (uint32_t)(ix >> 48);
+  if (ix - 0x3fee000000000000ull < 0x3090000000000ull) return log_near1(x);
+  if (top - 0x0010u >= 0x7ff0u - 0x0010u) return log_rare(x, T);
+  return log_core(ix, T);
 }
 
 /* ---- pow ------------------------------------------------------------------------------- */
