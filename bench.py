@@ -45,7 +45,9 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="exmouth")
-    ap.add_argument("--batches", type=int, default=8, help="row batches the scene is cut into (one per GPU per step)")
+    ap.add_argument("--batches", type=int, default=0,
+                    help="row batches the scene is cut into (one per GPU per step); default = --steps, so that the "
+                         "timed steps cover every batch of the scene exactly N times at N GPUs")
     ap.add_argument("--rows", type=int, default=0, help="debug: shrink the scene")
     ap.add_argument("--cols", type=int, default=0)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU work of the cpu_baseline sample")
@@ -158,7 +160,7 @@ def workload_config(spec, args, world, extra=None):
                      f"NBOTTOMS={spec.n_bottoms}, DEPTHS prior",
          "step": f"one batch of {rb} rows x {spec.ncols} cols per GPU ({args.batches} batches per scene), a new batch every step",
          "l2": "inputs larger than L2: every step reads a different batch (>=134 MB of planes)",
-         "parallelism": f"row bands x{world}" + (", NCCL halo exchange + gather" if world > 1 else "")}
+         "parallelism": f"row bands x{world}" + (", cost-balanced re-deal + halo exchange (NCCL p2p) + gather" if world > 1 else "")}
     if extra:
         c.update(extra)
     return c
@@ -166,6 +168,8 @@ def workload_config(spec, args, world, extra=None):
 
 def main():
     args = parse()
+    if args.batches <= 0:
+        args.batches = max(1, args.steps)
     if args.impl == "reference":
         return run_reference(args)
 
@@ -188,14 +192,14 @@ def main():
     K, W = args.steps, args.warmup
     halo = sharded.halo_rows(spec.n_spatial, spec.n_smoothing_radius)
     rb = -(-spec.nrows // args.batches)
-    plan = [(r * rb, (r + 1) * rb) for r in range(world)]  # row bands of the stacked per-step raster
+    plan_eq = [(r * rb, (r + 1) * rb) for r in range(world)]  # how the stacked per-step raster arrives
 
     # ---- resident inputs: the batches this rank will see, generated on the device ----------------
-    def batch_of(step):
-        return (step * world + rank) % args.batches
+    def batch_of(step, r=None):
+        return (step * world + (rank if r is None else r)) % args.batches
 
     need = sorted({batch_of(s) for s in range(W + K)})
-    data = {}
+    data, cost = {}, {}
     for b in need:
         r0, r1 = batch_rows(spec, args, b)
         p, pr = scene.generate(spec, r0, r1, device=dev)
@@ -204,19 +208,33 @@ def main():
             p = torch.cat([p, padp], dim=1).contiguous()
             pr = torch.cat([pr, torch.full((rb - (r1 - r0), spec.ncols), scene.NODATA, device=dev)], dim=0).contiguous()
         data[b] = (p, pr)
+        # estimated work per row: a shallow-water pixel (all substrates) costs ~3x a sand-only one
+        cost[b] = sharded.row_cost(scene.valid_mask(p), pr.abs() <= 8.0)
     torch.cuda.synchronize()
-    w0, w1, lb, le = sharded.window(plan[rank][0], plan[rank][1], halo, rb * world)
-    desc = capi.desc_from_spec(spec, nrows=w1 - w0)
-    outs = Inverter.alloc_device_outputs(desc, dev, scene_planes=False)
     peak_tflops, _ = inv.fp64_peak()
-
     gather_names = capi.SCALAR_PLANES
+    out_cache = {}
 
     def step(s):
+        """One step: N batches stacked into one raster; rows are re-dealt to cost-balanced bands (NCCL p2p),
+        halo rows exchanged, every rank inverts its band, the 9 result planes are gathered on rank 0."""
         p, pr = data[batch_of(s)]
+        plan = plan_eq
+        if world > 1:
+            c = torch.zeros(rb * world, device=dev)
+            c[rank * rb:(rank + 1) * rb] = cost[batch_of(s)]
+            dist.all_reduce(c)
+            plan = sharded.plan_row_bands(c.cpu().numpy(), world)
+            p = sharded.repartition_rows(p, plan_eq, plan, rank, world)
+            pr = sharded.repartition_rows(pr[None], plan_eq, plan, rank, world)[0]
         win = sharded.exchange_halo(p, plan, halo, rank, world)
         prw = sharded.exchange_halo(pr[None], plan, halo, rank, world)[0]
-        st = inv.invert_device(desc, win, prw, outs, row_begin=lb, row_end=le)
+        w0, w1, lb, le = sharded.window(plan[rank][0], plan[rank][1], halo, rb * world)
+        if w1 - w0 not in out_cache:
+            d = capi.desc_from_spec(spec, nrows=w1 - w0)
+            out_cache[w1 - w0] = (d, Inverter.alloc_device_outputs(d, dev, scene_planes=False))
+        desc, outs = out_cache[w1 - w0]
+        st = inv.invert_device(desc, win.contiguous(), prw.contiguous(), outs, row_begin=lb, row_end=le)
         if world > 1:
             stack = torch.stack([outs[n][lb:le] for n in gather_names])
             sharded.gather_bands(stack, plan, rank, world)

@@ -90,6 +90,42 @@ def exchange_halo(band: torch.Tensor, plan, halo: int, rank: int, world: int, gr
     return torch.cat(top + [band] + bot, dim=1).contiguous()
 
 
+def repartition_rows(band: torch.Tensor, plan_old, plan_new, rank: int, world: int, group=None) -> torch.Tensor:
+    """Moves rows between ranks so that a raster held as row bands `plan_old` is held as `plan_new`
+    (both lists of contiguous [r0, r1) covering the same rows). band: [planes, rows_old, cols].
+    Point-to-point sends of exactly the rows that change owner (NCCL over NVLink on a B200 box)."""
+    if world == 1 or list(plan_old) == list(plan_new):
+        return band
+    o0, o1 = plan_old[rank]
+    n0, n1 = plan_new[rank]
+    out = torch.empty((band.shape[0], n1 - n0, band.shape[2]), dtype=band.dtype, device=band.device)
+    a, b = max(o0, n0), min(o1, n1)
+    if b > a:  # rows that stay
+        out[:, a - n0:b - n0] = band[:, a - o0:b - o0]
+    ops = []
+    for other in range(world):
+        if other == rank:
+            continue
+        p0, p1 = plan_old[other]
+        q0, q1 = plan_new[other]
+        a, b = max(o0, q0), min(o1, q1)  # mine -> other's new band
+        if b > a:
+            ops.append(dist.P2POp(dist.isend, band[:, a - o0:b - o0].contiguous(), other, group))
+        a, b = max(p0, n0), min(p1, n1)  # other's old rows -> my new band
+        if b > a:
+            buf = torch.empty((band.shape[0], b - a, band.shape[2]), dtype=band.dtype, device=band.device)
+            ops.append(dist.P2POp(dist.irecv, buf, other, group))
+            ops.append(("copy", buf, a - n0, b - n0))
+    reqs = dist.batch_isend_irecv([o for o in ops if not isinstance(o, tuple)]) if any(not isinstance(o, tuple) for o in ops) else []
+    for r in reqs:
+        r.wait()
+    for o in ops:
+        if isinstance(o, tuple):
+            _, buf, x0, x1 = o
+            out[:, x0:x1] = buf
+    return out
+
+
 def gather_bands(local: torch.Tensor, plan, rank: int, world: int, dst: int = 0, group=None):
     """local: [..., r1-r0, cols] rows owned by this rank -> full [..., nrows, cols] on rank dst (None elsewhere).
     Bands differ in height, so they are padded to the tallest band for one all_gather."""

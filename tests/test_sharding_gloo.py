@@ -38,9 +38,13 @@ def _worker(rank, world, port, name, R, C, out_path):
     cost[e0:e1] = sharded.row_cost(scene.valid_mask(planes_eq), prior_eq.abs() <= 8.0)
     dist.all_reduce(cost)
     plan = sharded.plan_row_bands(cost.numpy(), world)
-    # phase 2: each rank holds ONLY its own rows; halo rows come from the neighbours
+    # phase 2: rows move from the equal split to the cost-balanced bands (point-to-point), then each rank
+    # holds ONLY its own rows; halo rows come from the neighbours
     r0, r1 = plan[rank]
-    planes, prior = scene.generate(spec, r0, r1)
+    planes = sharded.repartition_rows(planes_eq, eq, plan, rank, world)
+    prior = sharded.repartition_rows(prior_eq[None], eq, plan, rank, world)[0]
+    chk_p, chk_pr = scene.generate(spec, r0, r1)
+    assert torch.equal(planes, chk_p) and torch.equal(prior, chk_pr)
     win = sharded.exchange_halo(planes, plan, halo, rank, world)
     w0, w1, lb, le = sharded.window(r0, r1, halo, spec.nrows)
     assert win.shape[1] == w1 - w0
