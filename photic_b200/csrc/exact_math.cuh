@@ -128,6 +128,33 @@ PHM_HD double exp_core(double x, uint32_t abstop, const uint64_t *T) {
   return fma_(scale, tmp, scale);
 }
 
+/* Branch-free variant for the hot loop: valid iff exp_in_main_range(x); the caller tests that once per
+ * term and redoes the term through exp() otherwise. */
+PHM_HD bool exp_in_main_range(double x) {
+  uint32_t abstop = (uint32_t)(bits(x) >> 52) & 0x7ff;
+  return abstop - 0x3c9u < 0x3fu; /* 2^-54 <= |x| < 512 */
+}
+PHM_HD double exp_main(double x, const uint64_t *T) {
+  double kd = fma_(x, k::InvLn2N, k::Shift);
+  uint64_t ki = bits(kd);
+  kd = sub_(kd, k::Shift);
+  double r = fma_(kd, k::NegLn2hiN, x);
+  r = fma_(kd, k::NegLn2loN, r);
+  uint32_t idx = 2u * (uint32_t)(ki & 127u);
+  uint64_t top = ki << 45;
+  double tail = from_bits(T[idx]);
+  uint64_t sbits = T[idx + 1] + top;
+  double A = fma_(r, k::C3, k::C2);
+  double t = add_(r, tail);
+  double r2 = mul_(r, r);
+  double B = fma_(r, k::C5, k::C4);
+  double tmp = fma_(A, r2, t);
+  double r4 = mul_(r2, r2);
+  tmp = fma_(r4, B, tmp);
+  double scale = from_bits(sbits);
+  return fma_(scale, tmp, scale);
+}
+
 /* |x| < 2^-54 or |x| >= 512: rare, kept out of the hot instruction stream on the device */
 PHM_RARE double exp_rare(double x, const uint64_t *T) {
   uint64_t ix = bits(x);

@@ -295,8 +295,13 @@ static int invert_device_impl(phb_ctx *c, const phb_scene_desc *desc, const floa
   sp.L = make_layout(M.SB, M.n_scenes, M.n_bottoms, NrMax);
   const long long simplex_doubles = (long long)(sp.L.nmax + 1) * sp.L.nmax;
   const long long slab_doubles = simplex_doubles + sp.L.nmax + sp.L.Tmax;
+  /* kernel instantiation: compile-time substrate count for NBOTTOMS 1..3, run-time loop otherwise */
+  void (*kern)(const SolveParams) = solve_kernel<0>;
+  if (M.n_bottoms == 1) kern = solve_kernel<1>;
+  else if (M.n_bottoms == 2) kern = solve_kernel<2>;
+  else if (M.n_bottoms == 3) kern = solve_kernel<3>;
   cudaFuncAttributes fa0;
-  CK(cudaFuncGetAttributes(&fa0, solve_kernel));
+  CK(cudaFuncGetAttributes(&fa0, kern));
   const int W_reg = fa0.maxThreadsPerBlock / 32;
   const int W_smem = (int)(((long long)c->smem_optin - sp.L.cta_bytes) / sp.L.warp_bytes);
   if (W_smem < 1) return PHB_EINVAL; /* configuration does not fit shared memory */
@@ -324,9 +329,9 @@ static int invert_device_impl(phb_ctx *c, const phb_scene_desc *desc, const floa
   sp.dbg_capacity = dbg_cap;
   sp.counters = c->d_counters; sp.flops = c->d_flops;
   sp.exp_tab = c->d_exp_tab; sp.log_tab = c->d_log_tab; sp.pow_tab = c->d_pow_tab;
-  CK(cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   CK(cudaEventRecord(c->ev[2], st));
-  solve_kernel<<<ctas, W * 32, smem, st>>>(sp);
+  kern<<<ctas, W * 32, smem, st>>>(sp);
   {
     cudaError_t le = cudaGetLastError();
     if (le != cudaSuccess) {
@@ -354,9 +359,7 @@ static int invert_device_impl(phb_ctx *c, const phb_scene_desc *desc, const floa
     CK(cudaEventElapsedTime(&stats->ms_classify, c->ev[0], c->ev[1]));
     CK(cudaEventElapsedTime(&stats->ms_solve, c->ev[2], c->ev[3]));
     stats->warps_per_cta = W; stats->ctas = ctas; stats->smem_bytes = (int)smem;
-    cudaFuncAttributes fa;
-    CK(cudaFuncGetAttributes(&fa, solve_kernel));
-    stats->regs = fa.numRegs;
+    stats->regs = fa0.numRegs;
   }
   return PHB_OK;
 }
@@ -506,12 +509,12 @@ int phb_kat_objective(phb_ctx *c, const phb_scene_desc *desc, int nb_active, int
 }
 
 int phb_kat_math(phb_ctx *c, int fn, const double *x, const double *y, int64_t n, double *out) {
-  if (!c || !x || !out || n <= 0 || fn < 0 || fn > 2 || (fn == 2 && !y)) return PHB_EINVAL;
+  if (!c || !x || !out || n <= 0 || fn < 0 || fn > 7 || ((fn == 2 || fn == 3 || fn == 5) && !y)) return PHB_EINVAL;
   CK(cudaSetDevice(c->device));
   double *dx, *dy = nullptr, *dout;
   CK(cudaMalloc(&dx, n * 8)); CK(cudaMalloc(&dout, n * 8));
   CK(cudaMemcpy(dx, x, n * 8, cudaMemcpyHostToDevice));
-  if (fn == 2) { CK(cudaMalloc(&dy, n * 8)); CK(cudaMemcpy(dy, y, n * 8, cudaMemcpyHostToDevice)); }
+  if (y) { CK(cudaMalloc(&dy, n * 8)); CK(cudaMemcpy(dy, y, n * 8, cudaMemcpyHostToDevice)); }
   kat_math_kernel<<<c->n_sm * 4, 256>>>(fn, dx, dy, (long long)n, dout, c->d_exp_tab, c->d_log_tab, c->d_pow_tab);
   CK(cudaGetLastError());
   CK(cudaMemcpy(out, dout, n * 8, cudaMemcpyDeviceToHost));

@@ -168,6 +168,27 @@ def test_device_math_equals_host_libm(inverter):
     assert bits_equal(inverter.kat_math(2, x, y), np.array([math.pow(a, b) for a, b in zip(x, y)])).all()
 
 
+def test_branch_free_div_sqrt_exp_equal_ieee_operators(inverter):
+    """The hot loop uses nvcc's div/sqrt FAST PATHS without their range branch (one check per term instead).
+    Inside the guarded range they must equal the ordinary operators bit for bit; exp_main must equal exp."""
+    rng = np.random.default_rng(9)
+    n = 4_000_000
+    for lo, hi in ((-380.0, 380.0), (-30.0, 30.0), (-3.0, 3.0)):
+        a = np.exp2(rng.uniform(lo, hi, n)) * rng.choice([-1.0, 1.0], n)
+        b = np.exp2(rng.uniform(lo / 2, hi / 2, n)) * rng.choice([-1.0, 1.0], n)
+        assert bits_equal(inverter.kat_math(3, a, b), inverter.kat_math(5, a, b)).all()
+        x = np.abs(a)
+        assert bits_equal(inverter.kat_math(4, x), inverter.kat_math(6, x)).all()
+    u = rng.uniform(0.0, 1.0, n)   # the forward model's actual arguments
+    for c in (2.4, 5.4):
+        x = 1.0 + c * u
+        assert bits_equal(inverter.kat_math(4, x), inverter.kat_math(6, x)).all()
+    rho = rng.uniform(1e-6, 1.0, n)
+    assert bits_equal(inverter.kat_math(3, rho, np.full(n, 3.141592653589793)), inverter.kat_math(5, rho, np.full(n, 3.141592653589793))).all()
+    x = -np.exp(rng.uniform(np.log(2.0 ** -53), np.log(511.9), n))
+    assert bits_equal(inverter.kat_math(7, x), inverter.kat_math(0, x)).all()
+
+
 def test_refine_matches_oracle(inverter, oracle_port):
     """REFINE (model/refine.c): every flag combination against the CPU restatement, bit exact."""
     from photic_b200 import capi
