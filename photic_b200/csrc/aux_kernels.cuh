@@ -19,7 +19,7 @@ __global__ void kat_objective_kernel(const SolveParams p, int nb_active, int n_r
   bind_warp(w, p, phb_smem, 0, 0);
   Pixel px;
   px.Nr = n_regions; px.Nb = nb_active; px.origin = origin;
-  size_pixel(px, lane, SB, Ns, p.L.simplex_doubles);
+  size_pixel(px, lane, SB, Ns, p.L.simplex_doubles, 0);
   for (int t = lane; t < px.T; t += 32) w.meas[t] = meas[t];
   __syncwarp();
   phm::Tables tb;

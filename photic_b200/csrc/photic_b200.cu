@@ -317,6 +317,10 @@ static int invert_device_impl(phb_ctx *c, const phb_scene_desc *desc, const floa
   if (cache_bytes > simplex_doubles * 8) cache_bytes = simplex_doubles * 8;
   if (const char *e = getenv("PHB_SIMPLEX_SMEM_BYTES")) { long long v = atoll(e); if (v >= 0 && v < cache_bytes) cache_bytes = v; }
   add_simplex_cache(sp.L, (int)cache_bytes);
+  /* tensor memory (512 columns x 128 lanes per SM, idle on this path) holds the first simplex rows:
+   * warps sharing a lane quarter split the columns */
+  sp.L.tmem_cols = (512 / ((W + 3) / 4)) & ~1;
+  if (const char *e = getenv("PHB_TMEM")) { if (atoi(e) == 0) sp.L.tmem_cols = 0; }
   int ctas = c->n_sm;
   if (const char *e = getenv("PHB_CTAS")) { int v = atoi(e); if (v >= 1) ctas = v; }
   const size_t smem = (size_t)sp.L.cta_bytes + (size_t)W * sp.L.warp_bytes;
