@@ -32,7 +32,7 @@ __global__ void kat_objective_kernel(const SolveParams p, int nb_active, int n_r
   for (int v = 0; v < nvec; v++) {
     for (int i = lane; i < px.n; i += 32) w.xmin[i] = params[(size_t)v * px.n + i];
     __syncwarp();
-    const double e = objective<0>(w, px, lane, SB, Ns, p.L.NbMax, w.xmin, true, side);
+    const double e = objective<0, true>(w, px, lane, SB, Ns, p.L.NbMax, w.xmin, side);
     if (lane == 0) {
       double *o = out6 + (size_t)v * 6;
       o[0] = e; o[1] = side.e_rrs; o[2] = side.e_depth; o[3] = side.e_bottom; o[4] = side.e_K; o[5] = side.bottom_albedo;
@@ -57,7 +57,11 @@ __global__ void kat_math_kernel(int fn, const double *x, const double *y, long l
     else if (fn == 4) r = fast_sqrt(x[i]);
     else if (fn == 5) r = x[i] / y[i];                   /* ... against the ordinary IEEE operators */
     else if (fn == 6) r = sqrt(x[i]);
-    else r = phm::exp_main(x[i], tb.exp_tab);            /* 7: branch-free exp (valid in its main range) */
+    else if (fn == 7) r = exp_main_c(x[i], tb.exp_tab);  /* branch-free exp (valid in its main range) */
+    else if (fn == 8) r = div_by_pi(x[i]);               /* against x / pi */
+    else if (fn == 9) r = in_fast_range(x[i]) ? 1.0 : 0.0;
+    else if (fn == 10) r = exp_arg_in_main_range(x[i]) ? 1.0 : 0.0;
+    else r = unit_range(x[i]) ? 1.0 : 0.0;               /* 11 */
     out[i] = r;
   }
 }

@@ -187,6 +187,30 @@ def test_branch_free_div_sqrt_exp_equal_ieee_operators(inverter):
     assert bits_equal(inverter.kat_math(3, rho, np.full(n, 3.141592653589793)), inverter.kat_math(5, rho, np.full(n, 3.141592653589793))).all()
     x = -np.exp(rng.uniform(np.log(2.0 ** -53), np.log(511.9), n))
     assert bits_equal(inverter.kat_math(7, x), inverter.kat_math(0, x)).all()
+    # rho / pi with the reciprocal refined once per context (div_by_pi) == the IEEE quotient
+    pi = np.full(n, 3.141592653589793)
+    for lo, hi in ((-380.0, 380.0), (-30.0, 3.0)):
+        a = np.exp2(rng.uniform(lo, hi, n)) * rng.choice([-1.0, 1.0], n)
+        assert bits_equal(inverter.kat_math(8, a), inverter.kat_math(5, a, pi)).all()
+
+
+def test_range_predicates_of_the_hot_loop(inverter):
+    """The guards of the branch-free term read the high word of a double as a float (two FSETP each);
+    they must select exactly the sets the integer exponent tests define."""
+    rng = np.random.default_rng(10)
+    n = 2_000_000
+    bits = rng.integers(0, 2 ** 64, n, dtype=np.uint64)
+    edge = np.array([0x2800000000000000, 0x27ffffffffffffff, 0x5800000000000000, 0x57ffffffffffffff,
+                     0x3c90000000000000, 0x3c8fffffffffffff, 0x4080000000000000, 0x407fffffffffffff,
+                     0x3ff0000000000000, 0x3ff00000ffffffff, 0x3ff0000100000000, 0x8000000000000000, 0,
+                     0x7ff0000000000000, 0x7ff8000000000000, 0xfff8000000000000, 0x0000000000000001], dtype=np.uint64)
+    edge = np.concatenate([edge, edge | np.uint64(1 << 63)])
+    x = np.concatenate([bits, edge]).view(np.float64)
+    hi = (x.view(np.uint64) >> np.uint64(32)).astype(np.uint64)
+    e = (hi >> np.uint64(20)) & np.uint64(0x7ff)
+    assert np.array_equal(inverter.kat_math(9, x) == 1.0, (e >= 0x280) & (e < 0x580))
+    assert np.array_equal(inverter.kat_math(10, x) == 1.0, (e >= 0x3c9) & (e < 0x408))
+    assert np.array_equal(inverter.kat_math(11, x) == 1.0, hi <= 0x3ff00000)
 
 
 def test_refine_matches_oracle(inverter, oracle_port):
