@@ -300,11 +300,10 @@ static int invert_device_impl(phb_ctx *c, const phb_scene_desc *desc, const floa
   sp.L = make_layout(M.SB, M.n_scenes, M.n_bottoms, NrMax);
   const long long simplex_doubles = (long long)(sp.L.nmax + 1) * sp.L.nmax;
   const long long slab_doubles = simplex_doubles + sp.L.nmax + sp.L.Tmax;
-  /* kernel instantiation: compile-time substrate count for NBOTTOMS 1..3, run-time loop otherwise */
-  void (*kern)(const SolveParams) = solve_kernel<0>;
-  if (M.n_bottoms == 1) kern = solve_kernel<1>;
-  else if (M.n_bottoms == 2) kern = solve_kernel<2>;
-  else if (M.n_bottoms == 3) kern = solve_kernel<3>;
+  /* kernel instantiation: compile-time substrate count for the default NBOTTOMS 3, run-time loop otherwise;
+   * compile-time (scene,band) stride 32 (up to 8 dates x 4 bands) or the maximum */
+  void (*kern)(const SolveParams) = sp.L.SBP == 32 ? solve_kernel<0, 32> : solve_kernel<0, kMaxSB>;
+  if (M.n_bottoms == 3) kern = sp.L.SBP == 32 ? solve_kernel<3, 32> : solve_kernel<3, kMaxSB>; /* the default NBOTTOMS */
   cudaFuncAttributes fa0;
   CK(cudaFuncGetAttributes(&fa0, kern));
   const int W_reg = fa0.maxThreadsPerBlock / 32;
@@ -509,8 +508,10 @@ int phb_kat_objective(phb_ctx *c, const phb_scene_desc *desc, int nb_active, int
   CK(cudaMemcpy(d_meas, flat.data(), nm * 8, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(d_par, params, (size_t)nvec * nparams * 8, cudaMemcpyHostToDevice));
   const size_t smem = (size_t)sp.L.cta_bytes + sp.L.warp_bytes;
-  CK(cudaFuncSetAttribute(kat_objective_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kat_objective_kernel<<<1, 32, smem>>>(sp, nb_active, n_regions, origin, d_meas, nvec, d_par, d_out);
+  void (*kk)(const SolveParams, int, int, int, const double *, int, const double *, double *) =
+      sp.L.SBP == 32 ? kat_objective_kernel<32> : kat_objective_kernel<kMaxSB>;
+  CK(cudaFuncSetAttribute(kk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kk<<<1, 32, smem>>>(sp, nb_active, n_regions, origin, d_meas, nvec, d_par, d_out);
   CK(cudaGetLastError());
   CK(cudaMemcpy(out6, d_out, (size_t)nvec * 6 * 8, cudaMemcpyDeviceToHost));
   cudaFree(d_meas); cudaFree(d_par); cudaFree(d_out);
