@@ -299,7 +299,7 @@ static int invert_device_impl(phb_ctx *c, const phb_scene_desc *desc, const floa
   SolveParams sp;
   sp.L = make_layout(M.SB, M.n_scenes, M.n_bottoms, NrMax);
   const long long simplex_doubles = (long long)(sp.L.nmax + 1) * sp.L.nmax;
-  const long long slab_doubles = simplex_doubles + sp.L.nmax + sp.L.Tmax;
+  const long long slab_doubles = simplex_doubles + sp.L.nmax + sp.L.Tmax + (long long)((sp.L.nmax + 8) / 8 + 1) * sp.L.nmax; /* + centroid checkpoints */
   /* kernel instantiation: compile-time substrate count for the default NBOTTOMS 3, run-time loop otherwise;
    * compile-time (scene,band) stride 32 (up to 8 dates x 4 bands) or the maximum */
   void (*kern)(const SolveParams) = sp.L.SBP == 32 ? solve_kernel<0, 32> : solve_kernel<0, kMaxSB>;
@@ -492,7 +492,7 @@ int phb_kat_objective(phb_ctx *c, const phb_scene_desc *desc, int nb_active, int
   memset(&sp, 0, sizeof(sp));
   sp.L = make_layout(M.SB, M.n_scenes, nb_active, n_regions);
   if (nparams != sp.L.nmax) return PHB_EINVAL;
-  const long long slab_doubles = (long long)(sp.L.nmax + 1) * sp.L.nmax + sp.L.nmax + sp.L.Tmax;
+  const long long slab_doubles = (long long)(sp.L.nmax + 1) * sp.L.nmax + sp.L.nmax + sp.L.Tmax + (long long)((sp.L.nmax + 8) / 8 + 1) * sp.L.nmax;
   CK(c->slabs.ensure(slab_doubles));
   sp.M = c->d_model; sp.slabs = c->slabs.p; sp.slab_stride = slab_doubles;
   sp.exp_tab = c->d_exp_tab; sp.log_tab = c->d_log_tab; sp.pow_tab = c->d_pow_tab;
