@@ -74,6 +74,8 @@ typedef struct {
   double depth, K_min, iod, pct[PHO_MAX_BOTTOMS], P[PHO_MAX_SCENES], G[PHO_MAX_SCENES], X[PHO_MAX_SCENES];
   int bottom_type, converged, n_evals, n_iters;
   int variant;
+  int hot;                         /* md->start_at_previous */
+  double prev[3 * PHO_MAX_SCENES]; /* md->prev: |P|,|G|,|X| (x100) of the previous optimum, samodel.c:2086-2097 */
   const pho_model *m;
 } pho_pixel;
 
@@ -162,8 +164,10 @@ static float smoothed_sample(const float *plane, int i, int j, int nrows, int nc
   return acc / cnt;
 }
 
-/* samodel.c:2957-3027 with n_sigma = 0: gather the (2*n_spatial-1)^2 neighbourhood. */
-static void extract_region(pho_pixel *px, const float *planes, float nodata, int nrows, int ncols, int i, int j) {
+/* samodel.c:2957-3027: gather the (2*n_spatial-1)^2 neighbourhood; n_sigma * R_sigma[band] is added to every
+ * sample when n_sigma != 0 (the depth-error trials, samodel.c:3004-3006). */
+static void extract_region_noisy(pho_pixel *px, const float *planes, float nodata, int nrows, int ncols, int i, int j,
+                                 float n_sigma, const double *r_sigma, int maxb) {
   const pho_model *m = px->m;
   int nsp = m->n_spatial == 0 ? 1 : m->n_spatial, di, dj, s, b, kr = 0;
   for (di = 1 - nsp; di < nsp; di++) {
@@ -176,12 +180,17 @@ static void extract_region(pho_pixel *px, const float *planes, float nodata, int
           float v = smoothed_sample(planes + (size_t)g * nrows * ncols, ii, jj, nrows, ncols, m->n_smooth, nodata);
           if (pho_approx_equal(v, nodata, 1.0e-6f)) { missing = 1; break; }
           px->meas[kr][s][b] = (double)v;
+          if (!pho_approx_equal(n_sigma, 0.0f, 1.0e-6f)) px->meas[kr][s][b] += n_sigma * r_sigma[s * maxb + b];
         }
       if (i == ii && j == jj) px->origin = kr; /* samodel.c:3016: last clamped match wins */
       if (!missing) kr++;
     }
   }
   px->n_regions = kr;
+}
+
+static void extract_region(pho_pixel *px, const float *planes, float nodata, int nrows, int ncols, int i, int j) {
+  extract_region_noisy(px, planes, nodata, nrows, ncols, i, j, 0.0f, NULL, 0);
 }
 
 /* ------------------------------------------------------------------------------------------
@@ -567,6 +576,7 @@ static void optimise_one_combination(pho_pixel *px, double *params) {
   memset(best, 0, sizeof(best));
   h_quick[0] = px->h_prior;
   if (px->prior_present) { n_h = 1; h_start = h_quick; } else { n_h = 8; h_start = h_slow; }
+  if (px->hot) n_h = 1; /* samodel.c:2235-2241 (callers guarantee a prior: depth_prev is not modelled) */
 
   for (kh = 0; kh < n_h; kh++) {
     for (r = 0; r < Nr; r++) { start[r] = h_start[kh]; step[r] = 1.25 * start[r]; }
@@ -591,6 +601,11 @@ static void optimise_one_combination(pho_pixel *px, double *params) {
       start[off + 3 * s] = 100.0 * 0.072 * pow(mean490 / mean550, -1.7);
       start[off + 1 + 3 * s] = 1.5 * start[off + 3 * s];
       start[off + 2 + 3 * s] = 100.0 * 30.0 * m->aw640 * mean640;
+      if (px->hot) { /* samodel.c:2286-2309: P, G, X of the previous optimum */
+        start[off + 3 * s] = px->prev[3 * s];
+        start[off + 1 + 3 * s] = px->prev[3 * s + 1];
+        start[off + 2 + 3 * s] = px->prev[3 * s + 2];
+      }
       step[off + 3 * s] = 2.0 * start[off + 3 * s];
       step[off + 1 + 3 * s] = 2.0 * start[off + 1 + 3 * s];
       step[off + 2 + 3 * s] = 2.0 * start[off + 2 + 3 * s];
@@ -668,6 +683,9 @@ static void optimise_pixel(pho_pixel *px) {
     px->P[s] = 0.01 * fabs(best[off + 3 * s]);
     px->G[s] = 0.01 * fabs(best[off + 3 * s + 1]);
     px->X[s] = 0.01 * fabs(best[off + 3 * s + 2]);
+    px->prev[3 * s] = fabs(best[off + 3 * s]); /* samodel.c:2086-2097 */
+    px->prev[3 * s + 1] = fabs(best[off + 3 * s + 1]);
+    px->prev[3 * s + 2] = fabs(best[off + 3 * s + 2]);
   }
 }
 
@@ -919,5 +937,100 @@ int pho_refine(int nrows, int ncols, const float *in, float nodata, const float 
     }
     out[t] = depth;
   }
+  return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * depth-error estimate, samodel.c:1376-1477 (arguments as oracle/ref_harness.c:ref_depth_sigma)
+ * ---------------------------------------------------------------------------------------- */
+
+static int rand_below(int lo, int hi) { /* random_in_range, common.c:527-543: unbiased bucket of libc rand() */
+  for (;;) {
+    int v = rand(), range = hi - lo, rem = RAND_MAX % range, bucket = RAND_MAX / range;
+    if (v == RAND_MAX) continue;
+    if (v < RAND_MAX - rem) return lo + v / bucket;
+  }
+}
+static float rand_unit(void) { return ((float)rand()) / ((float)RAND_MAX); } /* frand, common.c:215 */
+static float rand_signed(float max) {                                         /* frand2, common.c:220-225 */
+  if (rand_unit() < 0.5) return ((float)rand()) / ((float)RAND_MAX / max);
+  return -1.0 * ((float)rand()) / ((float)RAND_MAX / max);
+}
+
+int pho_depth_sigma(int nscenes, int maxb, const int *n_bands, const int *wavelengths, const double *theta_v,
+                    const double *theta_w, const double *h_tide, const double *r_sigma, int n_smooth,
+                    int n_spatial, int n_bottoms, int nrows, int ncols, const float *planes, float nodata,
+                    const float *prior, float prior_nodata, const float *depth, unsigned seed, int n_samples,
+                    int chain_mode, int max_intervals, double *table, int *n_intervals_out, double *trials,
+                    float *depth_sigma) {
+  pho_model m;
+  pho_pixel *px;
+  double d, maxd, *td;
+  float mx = -PHO_BIG;
+  int n_trials, n_int, kd = 0, ks, kt, i = 0, j = 0, c;
+  size_t q;
+  if (prior == NULL || nscenes > PHO_MAX_SCENES || maxb > PHO_MAX_BANDS || n_bottoms > PHO_MAX_BOTTOMS ||
+      (2 * n_spatial - 1) * (2 * n_spatial - 1) > PHO_MAX_REGIONS)
+    return 1;
+  model_init(&m, nscenes, maxb, n_bands, wavelengths, theta_v, theta_w, h_tide, n_smooth, n_spatial, n_bottoms);
+  g_jitter = 0;
+  px = (pho_pixel *)calloc(1, sizeof(pho_pixel));
+  px->m = &m;
+  srand(seed);
+  n_trials = (int)sqrt(nrows * ncols);
+  for (q = 0; q < (size_t)nrows * ncols; q++) /* array_max2(depth, ., ., 0.0), common.c:1240-1258 */
+    if (!pho_approx_equal(depth[q], 0.0f, 1.0e-4f) && depth[q] > mx) mx = depth[q];
+  maxd = mx;
+  maxd = 0.25 * ((int)maxd / 0.25);
+  if (!(maxd < 30.0)) maxd = 30.0;
+  n_int = (int)maxd / 0.25;
+  if (n_int > max_intervals) { n_int = max_intervals; maxd = 0.25 * max_intervals; }
+  td = (double *)malloc(n_samples * sizeof(double));
+  px->hot = 0;
+  for (d = 0.0; d < maxd; d += 0.25) {
+    double total = 0.0, sumdev = 0.0, mean;
+    if (chain_mode == 1) px->hot = 0;
+    for (ks = 0; ks < n_samples; ks++) {
+      int found = 0;
+      float ns, e;
+      for (kt = 0; kt < n_trials; kt++) {
+        i = rand_below(0, nrows);
+        j = rand_below(0, ncols);
+        if (depth[(size_t)i * ncols + j] > d && depth[(size_t)i * ncols + j] < d + 0.25) { found = 1; break; }
+      }
+      if (!found) { td[ks] = 0.0; continue; }
+      ns = (float)(double)rand_signed(1.0); /* double n_sigma narrowed at the call, samodel.c:1425-1428 */
+      memset(px->K, 0, sizeof(px->K));
+      extract_region_noisy(px, planes, nodata, nrows, ncols, i, j, ns, r_sigma, maxb);
+      if (px->n_regions == 0) continue;
+      e = prior[(size_t)i * ncols + j];
+      if (pho_approx_equal(e, prior_nodata, 1.0e-6f)) { td[ks] = 0.0; continue; }
+      px->prior_present = 1;
+      px->h_prior = (e > -1.0) ? 1.0 : fabs(e);
+      optimise_pixel(px);
+      px->hot = 1;
+      td[ks] = px->depth;
+    }
+    if (trials) for (ks = 0; ks < n_samples; ks++) trials[(size_t)kd * n_samples + ks] = td[ks];
+    c = 0; /* vec_mean2_double returns FLOAT (common.c:877-893), vec_stddev_double common.c:924-941 */
+    for (ks = 0; ks < n_samples; ks++)
+      if (!pho_approx_equal((float)td[ks], 0.0f, 1.0e-4f)) { total += td[ks]; c++; }
+    mean = (c == 0) ? 0.0 : (double)(float)(total / ((double)c));
+    c = 0;
+    for (ks = 0; ks < n_samples; ks++)
+      if (!pho_approx_equal((float)td[ks], 0.0f, 1.0e-4f)) { sumdev += (td[ks] - mean) * (td[ks] - mean); c++; }
+    table[kd++] = (c == 0) ? 0.0 : sqrt(sumdev / ((double)c));
+  }
+  *n_intervals_out = kd;
+  if (depth_sigma)
+    for (q = 0; q < (size_t)nrows * ncols; q++) {
+      depth_sigma[q] = 0.0f;
+      if (depth[q] > 0.0) {
+        int k = 0;
+        for (d = 0.0; d < maxd; d += 0.25, k++)
+          if (depth[q] > d && depth[q] <= d + 0.25) { depth_sigma[q] = (float)table[k]; break; }
+      }
+    }
+  free(td); free(px);
   return 0;
 }

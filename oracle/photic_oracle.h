@@ -72,6 +72,15 @@ int pho_nelmin_kat(int fn_id, int n, const double *start, const double *step, do
 int pho_refine(int nrows, int ncols, const float *in, float nodata, const float *land, float land_nodata,
                const float *shallow, float shallow_nodata, int flags, const float *args, float *out);
 
+/* depth-error estimate of samodel() (samodel.c:1376-1477) with the seed as an argument; see
+ * oracle/ref_harness.c:ref_depth_sigma for the arguments */
+int pho_depth_sigma(int nscenes, int maxb, const int *n_bands, const int *wavelengths, const double *theta_v,
+                    const double *theta_w, const double *h_tide, const double *r_sigma, int n_smooth,
+                    int n_spatial, int n_bottoms, int nrows, int ncols, const float *planes, float nodata,
+                    const float *prior, float prior_nodata, const float *depth, unsigned seed, int n_samples,
+                    int chain_mode, int max_intervals, double *table, int *n_intervals_out, double *trials,
+                    float *depth_sigma);
+
 #ifdef __cplusplus
 }
 #endif

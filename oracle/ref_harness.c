@@ -14,6 +14,8 @@
  *   extract_Rrs_data  samodel.c:2957     samodel_optimise  samodel.c:1768
  *   samodel_error     samodel.c:2432     samodel_Rrs       samodel.c:2846
  *   nelmin            asa047.c:10        interp_1d         common.c:298
+ *   random_in_range   common.c:527       frand2            common.c:220
+ *   array_max2        common.c:1240      vec_mean2_double / vec_stddev_double  common.c:877,924
  *
  * The per-pixel "cold start" path (extract_Rrs_data -> h_empirical rule of
  * samodel.c:960-976 -> start_at_previous=false -> samodel_optimise) is the
@@ -427,5 +429,116 @@ int ref_samodel_as_is(int nscenes, int maxb, const int *n_bands, const int *wave
   for (g = 0; g < ngrids; g++) free(grids[g].array);
   if (prior) free(pg.array);
   free(grids);
+  return 0;
+}
+
+/*
+ * The depth-error phase of samodel() (samodel.c:1376-1477), driven with the reference's own functions:
+ * random_in_range / frand2 (libc rand()), extract_Rrs_data with the drawn n_sigma, samodel_optimise
+ * (hot-started from the previous trial once the first one has run), array_max2, vec_mean2_double,
+ * vec_stddev_double. The control flow of those hundred lines is restated here because it is inlined in
+ * samodel(); the reference seeds rand() with time(NULL) (samodel.c:371), here the seed is an argument.
+ * rand() is used nowhere else in samodel(), so this equals the reference run with srand(seed).
+ *   depth        [nrows*ncols] POSITIVE depths as the pixel loop leaves them (0 where nothing was inverted)
+ *   n_samples    128 in the reference (samodel.c:1378); smaller values keep tests short
+ *   chain_mode   0: one hot-start chain over all trials (the reference); 1: the chain restarts cold at
+ *                every depth interval (the parallel variant of the B200 path)
+ *   table        [n_intervals] sigma per 0.25 m interval;  trials (nullable) [n_intervals*n_samples]
+ *   depth_sigma  (nullable) [nrows*ncols]
+ * Requires a DEPTHS prior: without one a hot-started trial would start from md->depth_prev, which the
+ * reference leaves at whatever its LUT / hot-start bookkeeping wrote last (order dependent).
+ */
+int ref_depth_sigma(int nscenes, int maxb, const int *n_bands, const int *wavelengths, const double *theta_v,
+                    const double *theta_w, const double *h_tide, const double *r_sigma, int n_smooth,
+                    int n_spatial, int n_bottoms, int nrows, int ncols, const float *planes, float nodata,
+                    const float *prior, float prior_nodata, const float *depth_in, unsigned seed, int n_samples,
+                    int chain_mode, int max_intervals, double *table, int *n_intervals_out, double *trials,
+                    float *depth_sigma) {
+  ref_cfg c = {nscenes, maxb, n_bands, wavelengths, theta_v, theta_w, h_tide, r_sigma, n_smooth, n_spatial, n_bottoms};
+  int s, b, g = 0, r, ngrids = 0, i = 0, j = 0, k_sample, k_depth, k_trial, n_trials, n_depth_intervals;
+  double d, depth_interval, max_depth_reached, *trial_depths, mean_trial_depths, n_sigma;
+  bool within_interval;
+  scene *sc = (scene *)calloc(nscenes, sizeof(scene));
+  int *scene_indexes = (int *)malloc(nscenes * sizeof(int));
+  geogrid *grids;
+  float **depth;
+  model_data *md;
+  if (prior == NULL) return 1;
+  for (s = 0; s < nscenes; s++) ngrids += n_bands[s];
+  grids = (geogrid *)calloc(ngrids, sizeof(geogrid));
+  for (s = 0; s < nscenes; s++) {
+    scene_indexes[s] = s;
+    sc[s].n_bands = n_bands[s]; sc[s].nrows = nrows; sc[s].ncols = ncols;
+    sc[s].theta_v = theta_v[s]; sc[s].theta_w = theta_w[s]; sc[s].H_tide = h_tide[s];
+    for (b = 0; b < n_bands[s]; b++) {
+      sc[s].band_indexes[b] = g;
+      sc[s].wavelengths[b] = wavelengths[s * maxb + b];
+      sc[s].R_sigma[b] = r_sigma[s * maxb + b];
+      grids[g].nrows = nrows; grids[g].ncols = ncols; grids[g].nodata_value = nodata;
+      grids[g].array = (float **)malloc(nrows * sizeof(float *));
+      for (r = 0; r < nrows; r++) grids[g].array[r] = (float *)(planes + ((size_t)g * nrows + r) * ncols);
+      g++;
+    }
+  }
+  depth = (float **)malloc(nrows * sizeof(float *));
+  for (r = 0; r < nrows; r++) depth[r] = (float *)(depth_in + (size_t)r * ncols);
+  md = make_md(&c);
+
+  srand(seed); /* samodel.c:371 has time(NULL) */
+  n_trials = (int)sqrt(nrows * ncols);                                            /* samodel.c:1381 */
+  depth_interval = 0.25;
+  max_depth_reached = array_max2(depth, nrows, ncols, 0.0);                       /* samodel.c:1384-1387 */
+  max_depth_reached = depth_interval * ((int)max_depth_reached / depth_interval);
+  max_depth_reached = MIN(max_depth_reached, 30.0);
+  n_depth_intervals = (int)max_depth_reached / depth_interval;
+  if (n_depth_intervals > max_intervals) { n_depth_intervals = max_intervals; max_depth_reached = depth_interval * max_intervals; }
+  if (n_depth_intervals < 0) n_depth_intervals = 0;
+  trial_depths = (double *)malloc(n_samples * sizeof(double));
+  md->start_at_previous = false;
+  k_depth = 0;
+  for (d = 0.0; d < max_depth_reached; d += depth_interval) {                     /* samodel.c:1396-1461 */
+    if (chain_mode == 1) md->start_at_previous = false;
+    for (k_sample = 0; k_sample < n_samples; k_sample++) {
+      within_interval = false;
+      for (k_trial = 0; k_trial < n_trials; k_trial++) {
+        i = random_in_range(0, nrows);
+        j = random_in_range(0, ncols);
+        if (depth[i][j] > d && depth[i][j] < d + depth_interval) { within_interval = true; break; }
+      }
+      if (!within_interval) { trial_depths[k_sample] = 0.0; continue; }
+      n_sigma = frand2(1.0);
+      extract_Rrs_data(i, j, sc, grids, scene_indexes, nscenes, n_spatial, n_smooth, nrows, ncols, md, n_sigma);
+      if (md->n_regions == 0) continue;
+      if (!approx_equal(prior[(size_t)i * ncols + j], prior_nodata, 1.0e-6)) {
+        md->empirical_depth_present = true;
+        if (prior[(size_t)i * ncols + j] > -1.0) md->h_empirical = 1.0;
+        else md->h_empirical = fabs(prior[(size_t)i * ncols + j]);
+      } else { trial_depths[k_sample] = 0.0; continue; }
+      md->n_bottoms = n_bottoms;
+      samodel_optimise(md);
+      md->start_at_previous = true;
+      trial_depths[k_sample] = md->depth;
+    }
+    if (trials) for (k_sample = 0; k_sample < n_samples; k_sample++) trials[(size_t)k_depth * n_samples + k_sample] = trial_depths[k_sample];
+    mean_trial_depths = vec_mean2_double(trial_depths, n_samples, 0.0);
+    table[k_depth++] = vec_stddev_double(trial_depths, n_samples, 0.0, mean_trial_depths);
+  }
+  *n_intervals_out = k_depth;
+  if (depth_sigma) {                                                              /* samodel.c:1463-1477 */
+    for (i = 0; i < nrows; i++)
+      for (j = 0; j < ncols; j++) {
+        depth_sigma[(size_t)i * ncols + j] = 0.0;
+        if (depth[i][j] > 0.0) {
+          k_depth = 0;
+          for (d = 0.0; d < max_depth_reached; d += depth_interval) {
+            if (depth[i][j] > d && depth[i][j] <= d + depth_interval) { depth_sigma[(size_t)i * ncols + j] = table[k_depth]; break; }
+            k_depth++;
+          }
+        }
+      }
+  }
+  free(trial_depths); free(depth);
+  for (g = 0; g < ngrids; g++) free(grids[g].array);
+  free(grids); free(sc); free(scene_indexes);
   return 0;
 }
