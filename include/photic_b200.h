@@ -61,6 +61,8 @@ typedef struct phb_scene_desc {
   float nodata;                                       /* geogrid.nodata_value of the reflectance grids */
   int32_t prior_present;                              /* MODEL ... DEPTHS grid given (bam.c:3077)   */
   float prior_nodata;
+  double r_sigma[PHB_MAX_SCENES][PHB_MAX_BANDS];      /* scene.R_sigma (SCENE ... RSIGMA, bam.c:1474): only the
+                                                         depth-error trials read it (samodel.c:3004-3006)  */
 } phb_scene_desc;
 
 /*
@@ -123,6 +125,32 @@ int phb_invert_device(phb_ctx *ctx, const phb_scene_desc *desc, const float *d_p
 /* Same with HOST buffers: copies in, inverts, copies out (what the samodel() shim calls). */
 int phb_invert_host(phb_ctx *ctx, const phb_scene_desc *desc, const float *const *h_planes, const float *h_prior,
                     int row_begin, int row_end, const phb_outputs *h_out, phb_stats *stats);
+
+/*
+ * Depth-error estimate, the last phase of samodel() (samodel.c:1376-1477): for every 0.25 m depth interval
+ * up to min(floor(max depth), 30 m), `n_samples` (128 in the reference) pixels are drawn at random inside the
+ * interval (up to sqrt(nrows*ncols) probes each), re-inverted with every reflectance shifted by
+ * n_sigma * R_sigma[band], n_sigma ~ U(-1, 1), hot-started from the previous trial's P, G, X; the interval's
+ * sigma is the population standard deviation of the trial depths and every cell gets the sigma of its interval.
+ * The draws are libc rand() calls in the reference's order (random_in_range common.c:527, frand2 common.c:220);
+ * the reference seeds with time(NULL) (samodel.c:371), here the seed is an argument, so the reference run with
+ * srand(seed) produces the same table (tests pin that against oracle/_ref).
+ *   h_depth     [nrows][ncols] depth plane as phb_invert_* leaves it (NEGATED, -0 where nothing was inverted)
+ *   chain_mode  PHB_SIGMA_CHAIN_REFERENCE: one hot-start chain through all trials, as the reference runs them
+ *               (inherently serial: one warp works, ~10 ms per trial);
+ *               PHB_SIGMA_CHAIN_PER_INTERVAL: the chain restarts cold at every depth interval, intervals run
+ *               in parallel (the default of the samodel() shim; equals the reference modified the same way)
+ *   h_depth_sigma [nrows][ncols] out; table (nullable) [PHB_SIGMA_MAX_INTERVALS] out; trials (nullable)
+ *               [PHB_SIGMA_MAX_INTERVALS][n_samples] out: the trial depths (0 = no pixel found / no prior)
+ * A DEPTHS prior is required (PHB_EINVAL otherwise): without one the reference starts a hot trial from
+ * md->depth_prev, which depends on the order its pixel loop happened to run in.
+ */
+#define PHB_SIGMA_MAX_INTERVALS 120
+#define PHB_SIGMA_CHAIN_REFERENCE 0
+#define PHB_SIGMA_CHAIN_PER_INTERVAL 1
+int phb_depth_sigma_host(phb_ctx *ctx, const phb_scene_desc *desc, const float *const *h_planes, const float *h_prior,
+                         const float *h_depth, unsigned seed, int n_samples, int chain_mode, int max_intervals,
+                         float *h_depth_sigma, double *table, int32_t *n_intervals, double *trials, phb_stats *stats);
 
 /* Parity-test hook: like phb_invert_host but also returns the full-precision per-pixel record
  * (layout of oracle/ref_harness.c: 16 + n_scenes*max_bands + 3*n_scenes doubles) for every

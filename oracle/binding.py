@@ -164,6 +164,24 @@ class Oracle:
                                    C.c_float(prior_nodata), _p(out, _fp))
         return out
 
+    def depth_sigma(self, cfg, planes, nodata, prior, prior_nodata, depth_pos, seed, n_samples=128, chain_mode=0,
+                    max_intervals=120):
+        """Depth-error phase of samodel() (samodel.c:1376-1477) with the seed as an argument.
+        depth_pos: positive depths (0 where nothing was inverted). Returns (table, trials, depth_sigma)."""
+        planes, pr, dp = _f(planes), _f(prior), _f(depth_pos)
+        _, nrows, ncols = planes.shape
+        table = np.zeros(max_intervals)
+        trials = np.zeros((max_intervals, n_samples))
+        sig = np.zeros((nrows, ncols), dtype=np.float32)
+        nint = C.c_int(0)
+        rc = self._fn("depth_sigma")(*cfg.head(), C.c_int(cfg.n_smooth), C.c_int(cfg.n_spatial), C.c_int(cfg.n_bottoms),
+                                     C.c_int(nrows), C.c_int(ncols), _p(planes, _fp), C.c_float(nodata), _p(pr, _fp),
+                                     C.c_float(prior_nodata), _p(dp, _fp), C.c_uint(seed), C.c_int(n_samples),
+                                     C.c_int(chain_mode), C.c_int(max_intervals), _p(table, _dp), C.byref(nint),
+                                     _p(trials, _dp), _p(sig, _fp))
+        assert rc == 0, rc
+        return table[:nint.value], trials[:nint.value], sig
+
     def refine(self, grid, nodata, land, land_nodata, shallow, shallow_nodata, flags, args):
         assert self.kind == "port"
         grid = _f(grid)

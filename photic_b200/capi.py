@@ -37,6 +37,7 @@ class SceneDesc(C.Structure):
         ("nodata", C.c_float),
         ("prior_present", C.c_int32),
         ("prior_nodata", C.c_float),
+        ("r_sigma", (C.c_double * MAX_BANDS) * MAX_SCENES),
     ]
 
 
@@ -99,6 +100,9 @@ def lib() -> C.CDLL:
         L.phb_refine_host.argtypes = [C.c_void_p, _fp, C.c_float, _fp, C.c_float, _fp, C.c_float, C.c_int, C.c_int,
                                       C.c_int, _fp, _fp]
         L.phb_fp64_peak.argtypes = [C.c_void_p, _dp, _fp]
+        L.phb_depth_sigma_host.argtypes = [C.c_void_p, C.POINTER(SceneDesc), C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p,
+                                           C.c_uint, C.c_int, C.c_int, C.c_int, _fp, _dp, C.POINTER(C.c_int32), _dp,
+                                           C.POINTER(Stats)]
         _lib = L
     return _lib
 
@@ -106,7 +110,7 @@ def lib() -> C.CDLL:
 EXPORTS = ["phb_version", "phb_error_string", "phb_device_count", "phb_ctx_create", "phb_ctx_destroy",
            "phb_band_tables", "phb_invert_device", "phb_invert_host", "phb_debug_record_len", "phb_invert_host_debug",
            "phb_kat_objective", "phb_kat_math", "phb_refine_minmax_device", "phb_refine_device", "phb_refine_host",
-           "phb_fp64_peak"]
+           "phb_fp64_peak", "phb_depth_sigma_host"]
 
 
 def check(rc: int) -> None:
@@ -115,7 +119,7 @@ def check(rc: int) -> None:
 
 
 def make_desc(wavelengths, theta_view, theta_sun, h_tide, nrows, ncols, nodata=-9999.0, prior_present=True,
-              prior_nodata=-9999.0, n_smooth=1, n_spatial=2, n_bottoms=3) -> SceneDesc:
+              prior_nodata=-9999.0, n_smooth=1, n_spatial=2, n_bottoms=3, r_sigma=1.0e-4) -> SceneDesc:
     wl = np.asarray(wavelengths, dtype=np.int32)
     ns = len(theta_sun)
     if wl.ndim == 1:
@@ -127,6 +131,7 @@ def make_desc(wavelengths, theta_view, theta_sun, h_tide, nrows, ncols, nodata=-
         d.n_bands[s] = wl.shape[1]
         for b in range(wl.shape[1]):
             d.wavelengths[s][b] = int(wl[s, b])
+            d.r_sigma[s][b] = float(np.broadcast_to(np.asarray(r_sigma, dtype=np.float64), wl.shape)[s, b])
         d.theta_view[s] = float(tv[s])
         d.theta_sun[s] = float(theta_sun[s])
         d.h_tide[s] = float(h_tide[s])
@@ -143,4 +148,4 @@ def desc_from_spec(spec, nrows=None, prior_present=True) -> SceneDesc:
     return make_desc(spec.wavelengths, spec.theta_view, [spec.theta_sun(s) for s in range(ns)],
                      [spec.h_tide(s) for s in range(ns)], spec.nrows if nrows is None else nrows, spec.ncols,
                      prior_present=prior_present, n_smooth=spec.n_smoothing_radius, n_spatial=spec.n_spatial,
-                     n_bottoms=spec.n_bottoms)
+                     n_bottoms=spec.n_bottoms, r_sigma=spec.r_sigma)

@@ -34,6 +34,7 @@ struct ModelConst {
   double agexp[kMaxSB];    /* exp(-0.015*(lambda-440))   samodel.c:2891 */
   double ratio440[kMaxSB]; /* 440/lambda                 samodel.c:2903 */
   double bottom[kMaxK][kMaxSB];
+  double r_sigma[kMaxSB];  /* scene.R_sigma per (scene,band): depth-error trials only, samodel.c:3005 */
   double sec_view[kMaxS], sec_sun[kMaxS];
   double aw640;
   /* interp_1d (common.c:298) of the measured spectrum at 440/490/550/640 nm: bracket resolved

@@ -117,6 +117,7 @@ void build_model(const phb_scene_desc *d, ModelConst *M) {
       volatile double arg = -0.015 * (w - 440.0); /* -S*(lambda - 440.0), samodel.c:2891 */
       M->agexp[sb] = exp(arg);
       M->ratio440[sb] = 440.0 / w;
+      M->r_sigma[sb] = d->r_sigma[s][b];
     }
     for (int g = 0; g < 4; g++) {
       Bracket B = resolve_bracket(lam, d->n_bands[s], targets[g]);
@@ -262,6 +263,68 @@ int phb_debug_record_len(const phb_scene_desc *d) {
   return kRecHead + d->n_scenes * mb + 3 * d->n_scenes;
 }
 
+
+struct LaunchGeom { int W, ctas, smem, regs; };
+
+/* Shared-memory layout, launch geometry and launch of the persistent solve kernel (pixel queue or, trials = true,
+ * chains of depth-error trials). sp arrives with the work description filled in; the model, layout, slabs,
+ * counters and libm tables are bound here. */
+static int launch_solve(phb_ctx *c, const ModelConst &M, SolveParams &sp, bool trials, cudaStream_t st, LaunchGeom *geom) {
+  const int nsp = M.n_spatial == 0 ? 1 : M.n_spatial;
+  const int NrMax = (2 * nsp - 1) * (2 * nsp - 1);
+  sp.L = make_layout(M.SB, M.n_scenes, M.n_bottoms, NrMax);
+  const long long simplex_doubles = (long long)(sp.L.nmax + 1) * sp.L.nmax;
+  const long long slab_doubles = simplex_doubles + sp.L.nmax + sp.L.Tmax + (long long)((sp.L.nmax + 8) / 8 + 1) * sp.L.nmax; /* + centroid checkpoints */
+  /* kernel instantiation: compile-time substrate count for the default NBOTTOMS 3, run-time loop otherwise;
+   * compile-time (scene,band) stride 32 (up to 8 dates x 4 bands) or the maximum */
+  void (*kern)(const SolveParams) = sp.L.SBP == 32 ? solve_kernel<0, 32, false> : solve_kernel<0, kMaxSB, false>;
+  if (M.n_bottoms == 3) kern = sp.L.SBP == 32 ? solve_kernel<3, 32, false> : solve_kernel<3, kMaxSB, false>; /* the default NBOTTOMS */
+  if (trials) kern = sp.L.SBP == 32 ? solve_kernel<0, 32, true> : solve_kernel<0, kMaxSB, true>;
+  cudaFuncAttributes fa0;
+  CK(cudaFuncGetAttributes(&fa0, kern));
+  const int W_reg = fa0.maxThreadsPerBlock / 32;
+  const int W_smem = (int)(((long long)c->smem_optin - sp.L.cta_bytes) / sp.L.warp_bytes);
+  if (W_smem < 1) return PHB_EINVAL; /* configuration does not fit shared memory */
+  /* Occupancy vs simplex residency: each warp's leftover shared memory holds the first rows of its
+   * simplex (all of it for sand-only pixels); the rest lives in an L2-resident global slab. Default:
+   * 16 warps (4 per scheduler) when they fit; PHB_WARPS_PER_CTA overrides (tuning / profiling). */
+  int W = 16;
+  if (const char *e = getenv("PHB_WARPS_PER_CTA")) { int v = atoi(e); if (v >= 1) W = v; }
+  if (W > W_reg) W = W_reg;
+  if (W > W_smem) W = W_smem;
+  if (W < 1) W = 1;
+  long long cache_bytes = ((long long)c->smem_optin - sp.L.cta_bytes) / W - sp.L.warp_bytes;
+  if (cache_bytes > simplex_doubles * 8) cache_bytes = simplex_doubles * 8;
+  if (const char *e = getenv("PHB_SIMPLEX_SMEM_BYTES")) { long long v = atoll(e); if (v >= 0 && v < cache_bytes) cache_bytes = v; }
+  add_simplex_cache(sp.L, (int)cache_bytes);
+  /* tensor memory (512 columns x 128 lanes per SM, idle on this path) holds the first simplex rows:
+   * warps sharing a lane quarter split the columns */
+  sp.L.tmem_cols = (512 / ((W + 3) / 4)) & ~1;
+  if (const char *e = getenv("PHB_TMEM")) { if (atoi(e) == 0) sp.L.tmem_cols = 0; }
+  int ctas = c->n_sm;
+  if (const char *e = getenv("PHB_CTAS")) { int v = atoi(e); if (v >= 1) ctas = v; }
+  const size_t smem = (size_t)sp.L.cta_bytes + (size_t)W * sp.L.warp_bytes;
+  CK(c->slabs.ensure((size_t)ctas * W * slab_doubles));
+  sp.M = c->d_model;
+  sp.slabs = c->slabs.p; sp.slab_stride = slab_doubles;
+  sp.counters = c->d_counters; sp.flops = c->d_flops;
+  sp.exp_tab = c->d_exp_tab; sp.log_tab = c->d_log_tab; sp.pow_tab = c->d_pow_tab;
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<ctas, W * 32, smem, st>>>(sp);
+  {
+    cudaError_t le = cudaGetLastError();
+    if (le != cudaSuccess) {
+      char msg[256];
+      snprintf(msg, sizeof(msg), "solve_kernel launch (ctas=%d W=%d smem=%zu regs=%d maxThreads=%d): %s", ctas, W, smem,
+               fa0.numRegs, fa0.maxThreadsPerBlock, cudaGetErrorString(le));
+      g_last_cuda_error = msg;
+      return PHB_ECUDA;
+    }
+  }
+  if (geom) { geom->W = W; geom->ctas = ctas; geom->smem = (int)smem; geom->regs = fa0.numRegs; }
+  return PHB_OK;
+}
+
 static int invert_device_impl(phb_ctx *c, const phb_scene_desc *desc, const float *d_planes, const float *d_prior,
                               int row_begin, int row_end, const phb_outputs *d_out, cudaStream_t st, phb_stats *stats,
                               double *d_rec, int *d_pix, int *d_iters, long long dbg_cap) {
@@ -294,62 +357,17 @@ static int invert_device_impl(phb_ctx *c, const phb_scene_desc *desc, const floa
   CK(cudaGetLastError());
 
   /* solve */
-  const int nsp = M.n_spatial == 0 ? 1 : M.n_spatial;
-  const int NrMax = (2 * nsp - 1) * (2 * nsp - 1);
   SolveParams sp;
-  sp.L = make_layout(M.SB, M.n_scenes, M.n_bottoms, NrMax);
-  const long long simplex_doubles = (long long)(sp.L.nmax + 1) * sp.L.nmax;
-  const long long slab_doubles = simplex_doubles + sp.L.nmax + sp.L.Tmax + (long long)((sp.L.nmax + 8) / 8 + 1) * sp.L.nmax; /* + centroid checkpoints */
-  /* kernel instantiation: compile-time substrate count for the default NBOTTOMS 3, run-time loop otherwise;
-   * compile-time (scene,band) stride 32 (up to 8 dates x 4 bands) or the maximum */
-  void (*kern)(const SolveParams) = sp.L.SBP == 32 ? solve_kernel<0, 32> : solve_kernel<0, kMaxSB>;
-  if (M.n_bottoms == 3) kern = sp.L.SBP == 32 ? solve_kernel<3, 32> : solve_kernel<3, kMaxSB>; /* the default NBOTTOMS */
-  cudaFuncAttributes fa0;
-  CK(cudaFuncGetAttributes(&fa0, kern));
-  const int W_reg = fa0.maxThreadsPerBlock / 32;
-  const int W_smem = (int)(((long long)c->smem_optin - sp.L.cta_bytes) / sp.L.warp_bytes);
-  if (W_smem < 1) return PHB_EINVAL; /* configuration does not fit shared memory */
-  /* Occupancy vs simplex residency: each warp's leftover shared memory holds the first rows of its
-   * simplex (all of it for sand-only pixels); the rest lives in an L2-resident global slab. Default:
-   * 16 warps (4 per scheduler) when they fit; PHB_WARPS_PER_CTA overrides (tuning / profiling). */
-  int W = 16;
-  if (const char *e = getenv("PHB_WARPS_PER_CTA")) { int v = atoi(e); if (v >= 1) W = v; }
-  if (W > W_reg) W = W_reg;
-  if (W > W_smem) W = W_smem;
-  if (W < 1) W = 1;
-  long long cache_bytes = ((long long)c->smem_optin - sp.L.cta_bytes) / W - sp.L.warp_bytes;
-  if (cache_bytes > simplex_doubles * 8) cache_bytes = simplex_doubles * 8;
-  if (const char *e = getenv("PHB_SIMPLEX_SMEM_BYTES")) { long long v = atoll(e); if (v >= 0 && v < cache_bytes) cache_bytes = v; }
-  add_simplex_cache(sp.L, (int)cache_bytes);
-  /* tensor memory (512 columns x 128 lanes per SM, idle on this path) holds the first simplex rows:
-   * warps sharing a lane quarter split the columns */
-  sp.L.tmem_cols = (512 / ((W + 3) / 4)) & ~1;
-  if (const char *e = getenv("PHB_TMEM")) { if (atoi(e) == 0) sp.L.tmem_cols = 0; }
-  int ctas = c->n_sm;
-  if (const char *e = getenv("PHB_CTAS")) { int v = atoi(e); if (v >= 1) ctas = v; }
-  const size_t smem = (size_t)sp.L.cta_bytes + (size_t)W * sp.L.warp_bytes;
-  CK(c->slabs.ensure((size_t)ctas * W * slab_doubles));
-  sp.M = c->d_model; sp.planes = d_planes; sp.prior = cp.prior;
+  memset(&sp, 0, sizeof(sp));
+  sp.planes = d_planes; sp.prior = cp.prior;
   sp.queue = c->queue.p; sp.n_queue = c->d_scalars + 2; sp.head = c->d_scalars + 3;
-  sp.slabs = c->slabs.p; sp.slab_stride = slab_doubles;
   sp.out = *d_out;
   sp.dbg_rec = d_rec; sp.dbg_pix = d_pix; sp.dbg_iters = d_iters; sp.reclen = phb_debug_record_len(desc);
   sp.dbg_capacity = dbg_cap;
-  sp.counters = c->d_counters; sp.flops = c->d_flops;
-  sp.exp_tab = c->d_exp_tab; sp.log_tab = c->d_log_tab; sp.pow_tab = c->d_pow_tab;
-  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  LaunchGeom geom;
   CK(cudaEventRecord(c->ev[2], st));
-  kern<<<ctas, W * 32, smem, st>>>(sp);
-  {
-    cudaError_t le = cudaGetLastError();
-    if (le != cudaSuccess) {
-      char msg[256];
-      snprintf(msg, sizeof(msg), "solve_kernel launch (ctas=%d W=%d smem=%zu regs=%d maxThreads=%d): %s", ctas, W, smem,
-               fa0.numRegs, fa0.maxThreadsPerBlock, cudaGetErrorString(le));
-      g_last_cuda_error = msg;
-      return PHB_ECUDA;
-    }
-  }
+  rc = launch_solve(c, M, sp, false, st, &geom);
+  if (rc) return rc;
   CK(cudaEventRecord(c->ev[3], st));
 
   if (stats) {
@@ -366,8 +384,8 @@ static int invert_device_impl(phb_ctx *c, const phb_scene_desc *desc, const floa
     stats->alg_flops = fl;
     CK(cudaEventElapsedTime(&stats->ms_classify, c->ev[0], c->ev[1]));
     CK(cudaEventElapsedTime(&stats->ms_solve, c->ev[2], c->ev[3]));
-    stats->warps_per_cta = W; stats->ctas = ctas; stats->smem_bytes = (int)smem;
-    stats->regs = fa0.numRegs;
+    stats->warps_per_cta = geom.W; stats->ctas = geom.ctas; stats->smem_bytes = geom.smem;
+    stats->regs = geom.regs;
   }
   return PHB_OK;
 }
@@ -473,6 +491,168 @@ int phb_invert_host_debug(phb_ctx *ctx, const phb_scene_desc *desc, const float 
                           int row_begin, int row_end, const phb_outputs *h_out, double *rec, int32_t *pix,
                           int32_t *n_iters, int64_t capacity, phb_stats *stats) {
   return invert_host_impl(ctx, desc, h_planes, h_prior, row_begin, row_end, h_out, stats, rec, pix, n_iters, capacity);
+}
+
+
+/* ---- depth-error estimate (samodel.c:1376-1477) ----------------------------------------------------- */
+
+namespace {
+/* libc rand() draws exactly as the reference makes them */
+int rand_below(int lo, int hi) { /* random_in_range, common.c:527-543 */
+  for (;;) {
+    const int v = rand(), range = hi - lo, rem = RAND_MAX % range, bucket = RAND_MAX / range;
+    if (v == RAND_MAX) continue;
+    if (v < RAND_MAX - rem) return lo + v / bucket;
+  }
+}
+float rand_unit() { return ((float)rand()) / ((float)RAND_MAX); } /* frand, common.c:215 */
+float rand_signed(float max) {                                     /* frand2, common.c:220-225 */
+  if (rand_unit() < 0.5) return ((float)rand()) / ((float)RAND_MAX / max);
+  return -1.0 * ((float)rand()) / ((float)RAND_MAX / max);
+}
+}  // namespace
+
+int phb_depth_sigma_host(phb_ctx *c, const phb_scene_desc *desc, const float *const *h_planes, const float *h_prior,
+                         const float *h_depth, unsigned seed, int n_samples, int chain_mode, int max_intervals,
+                         float *h_depth_sigma, double *table, int32_t *n_intervals, double *trials, phb_stats *stats) {
+  if (!c || !h_planes || !h_depth || !h_depth_sigma) return PHB_EINVAL;
+  int rc = validate(desc);
+  if (rc) return rc;
+  if (!desc->prior_present || !h_prior) return PHB_EINVAL; /* see the header: hot trials need the DEPTHS prior */
+  if (n_samples < 1 || n_samples > 4096) return PHB_EINVAL;
+  if (max_intervals < 1 || max_intervals > PHB_SIGMA_MAX_INTERVALS) max_intervals = PHB_SIGMA_MAX_INTERVALS;
+  if (chain_mode != PHB_SIGMA_CHAIN_REFERENCE && chain_mode != PHB_SIGMA_CHAIN_PER_INTERVAL) return PHB_EINVAL;
+  CK(cudaSetDevice(c->device));
+  const int nrows = desc->nrows, ncols = desc->ncols;
+  const size_t px = (size_t)nrows * ncols;
+  int SB = 0;
+  for (int s = 0; s < desc->n_scenes; s++) SB += desc->n_bands[s];
+
+  /* interval table bounds, samodel.c:1381-1387 (depth here is the negated plane: -h_depth is the reference's) */
+  const int n_trials = (int)sqrt((double)(nrows * ncols));
+  float mx = -1.0e10f; /* array_max2(depth, ., ., 0.0), common.c:1240-1258 */
+  for (size_t q = 0; q < px; q++) {
+    const float dq = -h_depth[q];
+    if (!approx_equal_f(dq, 0.0f, 1.0e-4f) && dq > mx) mx = dq;
+  }
+  double maxd = mx;
+  if (!(maxd > 0.0)) maxd = 0.0; /* nothing inverted: no interval (the reference would index with (int)-1e10) */
+  maxd = 0.25 * ((int)maxd / 0.25);
+  if (!(maxd < 30.0)) maxd = 30.0;
+  int n_int = (int)((int)maxd / 0.25);
+  if (n_int > max_intervals) { n_int = max_intervals; maxd = 0.25 * max_intervals; }
+
+  /* the draws, in the reference's order (samodel.c:1396-1446) */
+  std::vector<int> t_pix, t_slot, chain_begin;
+  std::vector<float> t_nsig;
+  std::vector<double> td((size_t)(n_int > 0 ? n_int : 1) * n_samples, 0.0);
+  srand(seed);
+  int kd = 0;
+  chain_begin.push_back(0);
+  for (double d = 0.0; d < maxd; d += 0.25, kd++) {
+    for (int ks = 0; ks < n_samples; ks++) {
+      bool found = false;
+      int i = 0, j = 0;
+      for (int kt = 0; kt < n_trials; kt++) {
+        i = rand_below(0, nrows);
+        j = rand_below(0, ncols);
+        const float dq = -h_depth[(size_t)i * ncols + j];
+        if (dq > d && dq < d + 0.25) { found = true; break; }
+      }
+      if (!found) continue;                          /* trial_depths[k_sample] = 0 */
+      const float ns = (float)(double)rand_signed(1.0); /* drawn before the prior test, samodel.c:1425 */
+      if (approx_equal_f(h_prior[(size_t)i * ncols + j], desc->prior_nodata, 1.0e-6f)) continue;
+      t_pix.push_back(i * ncols + j);
+      t_nsig.push_back(ns);
+      t_slot.push_back(kd * n_samples + ks);
+    }
+    if (chain_mode == PHB_SIGMA_CHAIN_PER_INTERVAL && (int)t_pix.size() > chain_begin.back()) chain_begin.push_back((int)t_pix.size());
+  }
+  if (chain_mode == PHB_SIGMA_CHAIN_REFERENCE && !t_pix.empty()) chain_begin.push_back((int)t_pix.size());
+  const int n_tr = (int)t_pix.size(), n_chains = (int)chain_begin.size() - 1;
+
+  phb_stats local;
+  memset(&local, 0, sizeof(local));
+  if (n_tr > 0) {
+    cudaStream_t st = 0;
+    CK(c->planes.ensure(px * SB));
+    for (int g = 0; g < SB; g++)
+      CK(cudaMemcpyAsync(c->planes.p + g * px, h_planes[g], px * sizeof(float), cudaMemcpyHostToDevice, st));
+    CK(c->prior.ensure(px));
+    CK(cudaMemcpyAsync(c->prior.p, h_prior, px * sizeof(float), cudaMemcpyHostToDevice, st));
+    /* trial arrays: pix | chain_begin as ints, n_sigma as floats, depths as doubles */
+    CK(c->queue.ensure((size_t)n_tr + n_chains + 1));
+    CK(c->nev.ensure(n_tr));
+    CK(c->dbg_rec.ensure(n_tr));
+    CK(cudaMemcpyAsync(c->queue.p, t_pix.data(), n_tr * sizeof(int), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(c->queue.p + n_tr, chain_begin.data(), (n_chains + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(c->nev.p, t_nsig.data(), n_tr * sizeof(float), cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(c->dbg_rec.p, 0, n_tr * sizeof(double), st));
+    int sc[4] = {0, 0, n_chains, 0};
+    CK(cudaMemcpyAsync(c->d_scalars, sc, sizeof(sc), cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(c->d_counters, 0, 4 * sizeof(unsigned long long), st));
+    CK(cudaMemsetAsync(c->d_flops, 0, sizeof(double), st));
+    ModelConst M;
+    build_model(desc, &M);
+    CK(cudaMemcpyAsync(c->d_model, &M, sizeof(M), cudaMemcpyHostToDevice, st));
+    SolveParams sp;
+    memset(&sp, 0, sizeof(sp));
+    sp.planes = c->planes.p; sp.prior = c->prior.p;
+    sp.n_queue = c->d_scalars + 2; sp.head = c->d_scalars + 3;
+    sp.trial_pix = c->queue.p; sp.chain_begin = c->queue.p + n_tr;
+    sp.trial_nsig = reinterpret_cast<const float *>(c->nev.p);
+    sp.trial_depth = c->dbg_rec.p;
+    sp.reclen = phb_debug_record_len(desc);
+    LaunchGeom geom;
+    CK(cudaEventRecord(c->ev[2], st));
+    rc = launch_solve(c, M, sp, true, st, &geom);
+    if (rc) return rc;
+    CK(cudaEventRecord(c->ev[3], st));
+    std::vector<double> got(n_tr);
+    unsigned long long cnt[4];
+    double fl;
+    CK(cudaMemcpyAsync(got.data(), c->dbg_rec.p, n_tr * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(cnt, c->d_counters, sizeof(cnt), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&fl, c->d_flops, sizeof(fl), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    for (int t = 0; t < n_tr; t++) td[t_slot[t]] = got[t];
+    local.n_valid = n_tr; local.n_evals = (int64_t)cnt[0]; local.n_iters = (int64_t)cnt[1]; local.n_converged = (int64_t)cnt[2];
+    local.alg_flops = fl;
+    CK(cudaEventElapsedTime(&local.ms_solve, c->ev[2], c->ev[3]));
+    local.warps_per_cta = geom.W; local.ctas = geom.ctas; local.smem_bytes = geom.smem; local.regs = geom.regs;
+  }
+
+  /* per-interval statistics: vec_mean2_double (returns FLOAT, common.c:877-893) and vec_stddev_double
+   * (common.c:924-941, pow(.,2) of the host libm), spval 0 */
+  double tab[PHB_SIGMA_MAX_INTERVALS];
+  for (int k = 0; k < n_int; k++) {
+    const double *v = td.data() + (size_t)k * n_samples;
+    double total = 0.0, sumdev = 0.0;
+    int cnt = 0;
+    for (int q = 0; q < n_samples; q++)
+      if (!approx_equal_f((float)v[q], 0.0f, 1.0e-4f)) { total += v[q]; cnt++; }
+    const double mean = cnt == 0 ? 0.0 : (double)(float)(total / ((double)cnt));
+    cnt = 0;
+    for (int q = 0; q < n_samples; q++)
+      if (!approx_equal_f((float)v[q], 0.0f, 1.0e-4f)) { sumdev += pow(v[q] - mean, 2); cnt++; }
+    tab[k] = cnt == 0 ? 0.0 : sqrt(sumdev / ((double)cnt));
+  }
+  /* every cell gets the sigma of its interval (d, d + 0.25], samodel.c:1463-1477 */
+  for (size_t q = 0; q < px; q++) {
+    const float dq = -h_depth[q];
+    float sg = 0.0f;
+    if (dq > 0.0) {
+      int k = 0;
+      for (double d = 0.0; d < maxd; d += 0.25, k++)
+        if (dq > d && dq <= d + 0.25) { sg = (float)tab[k]; break; }
+    }
+    h_depth_sigma[q] = sg;
+  }
+  if (table) for (int k = 0; k < n_int; k++) table[k] = tab[k];
+  if (n_intervals) *n_intervals = n_int;
+  if (trials) memcpy(trials, td.data(), (size_t)n_int * n_samples * sizeof(double));
+  if (stats) *stats = local;
+  return PHB_OK;
 }
 
 /* ---- known-answer hooks ----------------------------------------------------------------------- */

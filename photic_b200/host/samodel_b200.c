@@ -29,6 +29,7 @@ typedef bool photic_bool;
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include "photic_b200.h"
 
@@ -96,6 +97,7 @@ void samodel(photic_scene scene_data[], photic_geogrid gridded_data[], int *scen
     d.h_tide[s] = sc->H_tide;
     for (b = 0; b < sc->n_bands; b++, g++) {
       d.wavelengths[s][b] = sc->wavelengths[b];
+      d.r_sigma[s][b] = sc->R_sigma[b];
       packed[g] = pack_rows(gridded_data[sc->band_indexes[b]].array, nrows, ncols);
       planes[g] = packed[g];
     }
@@ -141,8 +143,30 @@ void samodel(photic_scene scene_data[], photic_geogrid gridded_data[], int *scen
   grids9[4] = bottom_seagrass; grids9[5] = bottom_coral; grids9[6] = K_min; grids9[7] = bottom_type;
   grids9[8] = index_optical_depth;
   for (k = 0; k < 9; k++) unpack_rows(res[k], grids9[k], nrows, ncols);
-  for (r = 0; r < nrows; r++)
-    for (c = 0; c < ncols; c++) depth_sigma[r][c] = 0.0f;
+  /* depth-error estimate, samodel.c:1376-1477. The reference seeds rand() with time(NULL) (samodel.c:371);
+   * PHOTIC_B200_SIGMA_SEED fixes the seed, PHOTIC_B200_SIGMA_CHAIN=reference runs the trials as one serial
+   * hot-start chain exactly as the reference does (default: one chain per depth interval, in parallel). */
+  {
+    float *sig = (float *)malloc(px * sizeof(float));
+    if (sig == NULL) { printf("\n\nERROR: Out of memory.\n\n"); exit(1); }
+    memset(sig, 0, px * sizeof(float));
+    if (empirical_depth_present) {
+      const char *e_seed = getenv("PHOTIC_B200_SIGMA_SEED"), *e_chain = getenv("PHOTIC_B200_SIGMA_CHAIN");
+      const unsigned seed = e_seed ? (unsigned)strtoul(e_seed, NULL, 10) : (unsigned)time(NULL);
+      const int chain = (e_chain && strcmp(e_chain, "reference") == 0) ? PHB_SIGMA_CHAIN_REFERENCE : PHB_SIGMA_CHAIN_PER_INTERVAL;
+      phb_stats st2;
+      int32_t n_int = 0;
+      printf("\nComputing depth error estimates...");
+      rc = phb_depth_sigma_host(g_ctx, &d, planes, prior, res[0], seed, 128, chain, PHB_SIGMA_MAX_INTERVALS, sig, NULL,
+                                &n_int, NULL, &st2);
+      if (rc) die("depth error estimate failed", rc);
+      printf("...finished (%d depth intervals, %lld trials, %.1f ms).\n", (int)n_int, (long long)st2.n_valid, st2.ms_solve);
+    } else {
+      printf("\nDepth error estimates need a DEPTHS grid (see include/photic_b200.h): H_sigma left at 0.\n");
+    }
+    unpack_rows(sig, depth_sigma, nrows, ncols);
+    free(sig);
+  }
 
   /* file side effects of samodel.c:1494-1687, through the host's own NetCDF writer when present */
   if (write_nc) {

@@ -104,6 +104,24 @@ class Inverter:
             out["rec_iters"] = (it[:n, 1] >> 1)[order]
         return out, st.as_dict()
 
+    def depth_sigma_host(self, desc: SceneDesc, planes, prior, depth_neg, seed: int, n_samples: int = 128,
+                         chain_mode: int = 1, max_intervals: int = 120):
+        """Depth-error estimate of samodel() (samodel.c:1376-1477; phb_depth_sigma_host). ``depth_neg`` is the
+        depth plane as invert_* leaves it (negated). Returns (depth_sigma plane, table, trials, stats)."""
+        ptrs, keep = self._plane_ptrs(planes)
+        pr = np.ascontiguousarray(prior, dtype=np.float32)
+        dn = np.ascontiguousarray(depth_neg, dtype=np.float32)
+        sig = np.zeros((desc.nrows, desc.ncols), dtype=np.float32)
+        table = np.zeros(120)
+        trials = np.zeros((120, n_samples))
+        nint = C.c_int32(0)
+        st = Stats()
+        check(self.lib.phb_depth_sigma_host(self.ctx, C.byref(desc), ptrs, C.c_void_p(pr.ctypes.data),
+                                            C.c_void_p(dn.ctypes.data), C.c_uint(seed), n_samples, chain_mode,
+                                            max_intervals, _np_ptr(sig, capi._fp), _np_ptr(table, capi._dp),
+                                            C.byref(nint), _np_ptr(trials, capi._dp), C.byref(st)))
+        return sig, table[:nint.value], trials[:nint.value], st.as_dict()
+
     # ---- device buffers (resident data: bench `value`, multi-GPU shards) ---------------------------
     def invert_device(self, desc: SceneDesc, planes, prior, outputs: dict, row_begin=0, row_end=None, stream=None):
         """planes / prior / outputs are torch CUDA tensors on this device. Returns stats dict."""
@@ -221,12 +239,13 @@ _default_inverter = None
 def samodel(scene_data, gridded_data, scene_indexes, nscenes, empirical_depth_present, empirical_depths,
             n_smoothing_radius, n_spatial, n_bottoms, depth, depth_sigma, model_error, bottom_albedo, bottom_sand,
             bottom_seagrass, bottom_coral, K_min, bottom_type, index_optical_depth, pagesize=8.0, background=0,
-            linewidth=1, inverter: Inverter | None = None):
+            linewidth=1, inverter: Inverter | None = None, sigma_seed: int | None = None, sigma_chain: int = 1):
     """Same arguments as the reference's samodel(); the ten output grids are filled in place.
 
     Differences from the reference, all documented in DESIGN.md: every valid pixel is inverted from
-    a cold start (no LUT / hot start, which make the reference order dependent); depth_sigma is
-    left at 0 (its Monte-Carlo pass is seeded by time(NULL) in the reference).
+    a cold start (no LUT / hot start, which make the reference order dependent); the depth-error
+    pass (depth_sigma, samodel.c:1376-1477) takes its seed as an argument (time() when None, like the
+    reference) and needs the DEPTHS grid (0 without one).
     Returns the stats dict (the reference returns nothing).
     """
     global _default_inverter
@@ -241,7 +260,9 @@ def samodel(scene_data, gridded_data, scene_indexes, nscenes, empirical_depth_pr
                           [s.theta_w for s in scs], [s.H_tide for s in scs], g0.nrows, g0.ncols,
                           nodata=g0.nodata_value, prior_present=bool(empirical_depth_present),
                           prior_nodata=empirical_depths.nodata_value if empirical_depth_present else -9999.0,
-                          n_smooth=n_smoothing_radius, n_spatial=n_spatial, n_bottoms=n_bottoms)
+                          n_smooth=n_smoothing_radius, n_spatial=n_spatial, n_bottoms=n_bottoms,
+                          r_sigma=np.array([[(s.R_sigma[b] if b < len(s.R_sigma) else 0.0) for b in range(s.n_bands)]
+                                            for s in scs]))
     planes = [gridded_data[k].array for s in scs for k in s.band_indexes]
     buffers = {"depth": depth, "model_error": model_error, "bottom_albedo": bottom_albedo, "bottom_sand": bottom_sand,
                "bottom_seagrass": bottom_seagrass, "bottom_coral": bottom_coral, "K_min": K_min,
@@ -251,5 +272,12 @@ def samodel(scene_data, gridded_data, scene_indexes, nscenes, empirical_depth_pr
     out, stats = inv.invert_host(desc, planes, empirical_depths.array if empirical_depth_present else None,
                                  buffers=buffers)
     depth_sigma[...] = 0.0
+    if empirical_depth_present:
+        import time
+        seed = int(time.time()) if sigma_seed is None else int(sigma_seed)
+        sig, table, _, st2 = inv.depth_sigma_host(desc, planes, empirical_depths.array, depth, seed & 0xFFFFFFFF, 128,
+                                                  sigma_chain)
+        depth_sigma[...] = sig
+        stats["sigma_intervals"], stats["sigma_trials"], stats["sigma_ms"] = len(table), st2["n_valid"], st2["ms_solve"]
     samodel.last_outputs = out
     return stats

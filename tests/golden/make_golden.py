@@ -110,5 +110,40 @@ def main():
     print("done")
 
 
+def make_depth_sigma():
+    """Depth-error phase (samodel.c:1376-1477) through the reference's own functions with srand(seed):
+    one hot-start chain (the reference) and the chain restarted at every interval."""
+    build()
+    ref = Oracle("reference")
+    spec = scene.CONFIGS["murion"].scaled(40, 32)
+    planes, prior = scene.generate(spec)
+    planes, prior = planes.numpy(), prior.numpy()
+    cfg = SceneCfg.from_spec(spec)
+    import torch
+    ii, jj = np.nonzero(scene.valid_mask(torch.from_numpy(planes)).numpy())
+    out = ref.invert_pixels(cfg, planes, scene.NODATA, prior, scene.NODATA, ii, jj, nthreads=8)
+    depth = np.zeros((spec.nrows, spec.ncols), dtype=np.float32)
+    depth[ii, jj] = out["rec"][:, 0].astype(np.float32)  # (float) md->depth, samodel.c:1120
+    prior[ii[3], jj[3]] = scene.NODATA                    # a valid pixel without prior: its trials score 0
+    seed, n_samples, max_int = 20261017, 16, 40
+    res = {}
+    for mode in (0, 1):
+        table, trials, sig = ref.depth_sigma(cfg, planes, scene.NODATA, prior, scene.NODATA, depth, seed, n_samples, mode,
+                                             max_int)
+        res[f"table{mode}"], res[f"trials{mode}"], res[f"sigma{mode}"] = table, trials, sig
+        print("depth_sigma mode", mode, "intervals", len(table), "trials run", int((trials != 0).sum()), "sigma>0 cells",
+              int((sig > 0).sum()))
+    np.savez_compressed(
+        os.path.join(HERE, "depth_sigma_murion.npz"), planes=planes, prior=prior, depth=depth, seed=seed,
+        n_samples=n_samples, max_intervals=max_int, wavelengths=np.array(spec.wavelengths), theta_view=spec.theta_view,
+        theta_sun=np.array([spec.theta_sun(s) for s in range(spec.n_dates)]),
+        h_tide=np.array([spec.h_tide(s) for s in range(spec.n_dates)]), n_smooth=spec.n_smoothing_radius,
+        n_spatial=spec.n_spatial, n_bottoms=spec.n_bottoms, nodata=scene.NODATA, use_prior=True, **res)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "depth_sigma":
+        make_depth_sigma()
+    else:
+        main()
+        make_depth_sigma()

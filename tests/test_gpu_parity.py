@@ -213,6 +213,21 @@ def test_range_predicates_of_the_hot_loop(inverter):
     assert np.array_equal(inverter.kat_math(11, x) == 1.0, hi <= 0x3ff00000)
 
 
+@pytest.mark.parametrize("mode", [0, 1])
+def test_depth_sigma_matches_reference(inverter, mode):
+    """phb_depth_sigma_host (samodel.c:1376-1477 on the GPU: host-side libc draws, trial chains on the device)
+    against the golden run of the reference's own functions with the same seed: every trial depth, the sigma
+    table and the sigma plane, bit for bit."""
+    g = load_golden("depth_sigma_murion")
+    desc = desc_from_golden(g)
+    sig, table, trials, st = inverter.depth_sigma_host(desc, g["planes"], g["prior"], -g["depth"], int(g["seed"]),
+                                                       int(g["n_samples"]), mode, int(g["max_intervals"]))
+    assert st["n_valid"] == (g[f"trials{mode}"] != 0).sum() > 50
+    assert bits_equal(trials, g[f"trials{mode}"]).all()
+    assert bits_equal(table, g[f"table{mode}"]).all()
+    assert np.array_equal(sig.view(np.int32), g[f"sigma{mode}"].view(np.int32))
+
+
 def test_refine_matches_oracle(inverter, oracle_port):
     """REFINE (model/refine.c): every flag combination against the CPU restatement, bit exact."""
     from photic_b200 import capi
@@ -242,5 +257,9 @@ def test_python_samodel_surface(inverter):
     scenes = [scene(f"d{s}", [4 * s + b for b in range(4)], list(spec.wavelengths), spec.theta_view, spec.theta_sun(s),
                     spec.h_tide(s)) for s in range(spec.n_dates)]
     outs = [np.zeros((16, 12), dtype=np.float32) for _ in range(10)]
-    st = samodel(scenes, grids, list(range(spec.n_dates)), spec.n_dates, True, grids[-1], 1, 2, 3, *outs, inverter=inverter)
+    for s in scenes:
+        s.R_sigma = [spec.r_sigma] * 4
+    st = samodel(scenes, grids, list(range(spec.n_dates)), spec.n_dates, True, grids[-1], 1, 2, 3, *outs, inverter=inverter,
+                 sigma_seed=5)
     assert st["n_valid"] > 0 and (outs[0] <= 0).all() and (outs[0] < 0).sum() == st["n_valid"]
+    assert st["sigma_trials"] > 0 and (outs[1] >= 0).all() and (outs[1][outs[0] == 0] == 0).all()

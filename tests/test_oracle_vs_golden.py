@@ -94,3 +94,19 @@ def test_sensitivity_what_if_documents_why_bit_exactness_is_needed(oracle_port):
     c = oracle_port.invert_pixels(*args, variant=1)      # tree-summed residuals
     close = np.abs(c["rec"][:, 0] - a["rec"][:, 0]) < 1e-3
     assert close.mean() > 0.9                            # mostly the same answers, but no guarantee of all
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_depth_sigma_matches_reference_golden(oracle_port, mode):
+    """Depth-error phase of samodel() (samodel.c:1376-1477): the restatement, seeded like the golden run of the
+    reference's own functions, reproduces every trial depth, the sigma table and the sigma plane bit for bit
+    (mode 0: the reference's single hot-start chain; mode 1: chain restarted at every depth interval)."""
+    g = load_golden("depth_sigma_murion")
+    cfg = cfg_from_golden(g)
+    table, trials, sig = oracle_port.depth_sigma(cfg, g["planes"], float(g["nodata"]), g["prior"], float(g["nodata"]),
+                                                 g["depth"], int(g["seed"]), int(g["n_samples"]), mode,
+                                                 int(g["max_intervals"]))
+    assert (g[f"trials{mode}"] != 0).sum() > 50
+    assert bits_equal(trials, g[f"trials{mode}"]).all()
+    assert bits_equal(table, g[f"table{mode}"]).all()
+    assert np.array_equal(sig.view(np.int32), g[f"sigma{mode}"].view(np.int32))
