@@ -164,7 +164,7 @@ int phb_invert_host_debug(phb_ctx *ctx, const phb_scene_desc *desc, const float 
  * parameter vectors, mirroring oracle/ref_harness.c:ref_error_kat) and of the exact libm port. */
 int phb_kat_objective(phb_ctx *ctx, const phb_scene_desc *desc, int n_bottoms_active, int n_regions, int origin,
                       const double *rrs_measured, int nparams, int nvec, const double *params, double *out6);
-int phb_kat_math(phb_ctx *ctx, int fn /*0 exp,1 log,2 pow,3 fast_div,4 fast_sqrt,5 a/b,6 sqrt,7 exp_main,8 x/pi fast,9-11 range predicates*/, const double *x,
+int phb_kat_math(phb_ctx *ctx, int fn /*0 exp,1 log,2 pow,3 fast_div,4 fast_sqrt,5 a/b,6 sqrt,7 exp_main,8 x/pi fast,9-11 range predicates,12 log10*/, const double *x,
                  const double *y, int64_t n, double *out);
 
 /*
@@ -186,6 +186,18 @@ int phb_refine_device(phb_ctx *ctx, const float *d_in, float nodata, const float
 int phb_refine_host(phb_ctx *ctx, const float *h_in, float nodata, const float *h_land, float land_nodata,
                     const float *h_shallow, float shallow_nodata, int nrows, int ncols, int flags, const float *args,
                     float *h_out);
+
+/*
+ * MODEL Lee_Kd_LS8 / MODEL Lee_Secchi_LS8 (bam.c:3250-3610 -> Kd_LS8 secchi.c:13, secchi_disk_depth secchi.c:59):
+ * Lee et al. (2016) diffuse attenuation (mode 0: min over Kd(443,481,530,554,656)) and Secchi-disk depth (mode 1)
+ * from the coastal / blue / green / red Landsat-8 reflectance planes; these feed the scene-level priors upstream
+ * of samodel(). spv: nodata of the four planes; a cell with any nodata gets spv[0].
+ * theta_s: solar zenith in degrees as the reference passes it. Point-wise, bit-identical to the CPU.
+ */
+int phb_lee_ls8_device(phb_ctx *ctx, int mode, const float *d_coastal, const float *d_blue, const float *d_green,
+                       const float *d_red, const float *spv, float theta_s, int64_t n, float *d_out, void *stream);
+int phb_lee_ls8_host(phb_ctx *ctx, int mode, const float *h_coastal, const float *h_blue, const float *h_green,
+                     const float *h_red, const float *spv, float theta_s, int nrows, int ncols, float *h_out);
 
 /* FP64 pipe peak of this device, measured with a dependent-free DFMA chain kernel (MEASURED_PEAKS.json
  * has no FP64 entry). Returns TFLOP/s (2 flops per DFMA) and the kernel time. */

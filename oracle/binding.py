@@ -182,6 +182,15 @@ class Oracle:
         assert rc == 0, rc
         return table[:nint.value], trials[:nint.value], sig
 
+    def lee_ls8(self, mode, coastal, blue, green, red, spv, theta_s):
+        """MODEL Lee_Kd_LS8 (mode 0) / Lee_Secchi_LS8 (mode 1) on four float32 planes (secchi.c:13-252)."""
+        pl = [_f(a) for a in (coastal, blue, green, red)]
+        out = np.zeros_like(pl[0])
+        sp = _f(spv)
+        self._fn("lee_ls8")(C.c_int(mode), C.c_int(out.shape[0]), C.c_int(out.shape[1]), *[_p(a, _fp) for a in pl],
+                            _p(sp, _fp), C.c_float(theta_s), _p(out, _fp))
+        return out
+
     def refine(self, grid, nodata, land, land_nodata, shallow, shallow_nodata, flags, args):
         assert self.kind == "port"
         grid = _f(grid)

@@ -1034,3 +1034,72 @@ int pho_depth_sigma(int nscenes, int maxb, const int *n_bands, const int *wavele
   free(td); free(px);
   return 0;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * MODEL Lee_Kd_LS8 / Lee_Secchi_LS8: Lee et al. 2016 QAA-style Kd and Secchi depth for Landsat-8
+ * (secchi.c:13-252). Arguments as oracle/ref_harness.c:ref_lee_ls8.
+ * ---------------------------------------------------------------------------------------- */
+#undef exp
+#undef log
+#undef pow
+
+/* Lee_Kd_LS8, secchi.c:117-252: inputs and outputs are floats, the arithmetic is double */
+static void lee_kd_bands(float R443, float R481, float R554, float R656, float theta_s, float *kd) {
+  const double g0 = 0.0895, g1 = 0.1247, aw = 0.05866, h0 = -1.146, h1 = -1.366, h2 = 0.469;
+  const double bbw[4] = {0.00244761, 0.00171397, 0.000931339, 0.000448682};
+  const double lam[4] = {443.0, 481.0, 554.0, 656.0};
+  const double m0 = 0.005, m1 = 4.26, m2 = 0.52, m3 = 10.8, gamma = 0.265;
+  const float Rrs[4] = {R443, R481, R554, R656};
+  double rrs[4], u[4], a[4], bb[4], bbp[4], chi, eta;
+  int b;
+  for (b = 0; b < 4; b++) {
+    rrs[b] = Rrs[b] / (0.52 + 1.7 * Rrs[b]);
+    u[b] = (-g0 + sqrt(g0 * g0 + 4.0 * g1 * rrs[b])) / (2.0 * g1);
+  }
+  chi = log10((rrs[0] + rrs[1]) / (rrs[2] + 5.0 * rrs[3] * rrs[3] / rrs[1]));
+  a[2] = aw + pow(10.0, h0 + h1 * chi + h2 * chi * chi);
+  bb[2] = (-a[2] * g0 + 2.0 * a[2] * rrs[2] + a[2] * sqrt(g0 * g0 + 4.0 * g1 * rrs[2])) / (2.0 * (g0 + g1 - rrs[2]));
+  bbp[2] = (u[2] * a[2]) / (1 - u[2]) - bbw[2];
+  eta = 2.0 * (1.0 - 1.2 * exp(-0.9 * rrs[0] / rrs[2]));
+  for (b = 0; b < 4; b++) {
+    if (b == 2) continue;
+    bbp[b] = bbp[2] * pow(554.0 / lam[b], eta);
+    a[b] = (1.0 - u[b]) * (bbw[b] + bbp[b]) / u[b];
+    bb[b] = (-a[b] * g0 + 2.0 * a[b] * rrs[b] + a[b] * sqrt(g0 * g0 + 4.0 * g1 * rrs[b])) / (2.0 * (g0 + g1 - rrs[b]));
+  }
+  for (b = 0; b < 4; b++) {
+    double kk1 = (1.0 + m0 * theta_s) * a[b];
+    double kk2 = m1 * (1.0 - gamma * bbw[b] / bb[b]);
+    double kk3 = (1.0 - m2 * exp(-m3 * a[b])) * bb[b];
+    kd[b] = kk1 + kk2 * kk3;
+  }
+}
+
+static float lee_kd_min(const float *k4) { /* secchi.c:45-52, 100-109: Kd(530) = 0.20 Kd_blue + 0.75 Kd_green; vec_min */
+  float kd[5], mn;
+  int q;
+  kd[0] = k4[0]; kd[1] = k4[1]; kd[2] = 0.20 * k4[1] + 0.75 * k4[2]; kd[3] = k4[2]; kd[4] = k4[3];
+  mn = kd[0];
+  for (q = 0; q < 5; q++) if (kd[q] < mn) mn = kd[q];
+  return mn;
+}
+
+int pho_lee_ls8(int mode, int nrows, int ncols, const float *coastal, const float *blue, const float *green,
+                const float *red, const float *spv, float theta_s, float *out) {
+  size_t q, n = (size_t)nrows * ncols;
+  for (q = 0; q < n; q++) {
+    float k4[4], kmin;
+    if (!(coastal[q] != spv[0] && blue[q] != spv[1] && green[q] != spv[2] && red[q] != spv[3])) { out[q] = spv[0]; continue; }
+    lee_kd_bands(coastal[q], blue[q], green[q], red[q], theta_s, k4);
+    kmin = lee_kd_min(k4);
+    if (mode == 0) out[q] = kmin;
+    else { /* Lee_secchi_LS8, secchi.c:86-114 */
+      float mx = coastal[q];
+      if (blue[q] > mx) mx = blue[q];
+      if (green[q] > mx) mx = green[q];
+      if (red[q] > mx) mx = red[q];
+      out[q] = log(fabs(0.14 - mx) / 0.013) / (2.5 * kmin);
+    }
+  }
+  return 0;
+}

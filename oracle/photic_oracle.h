@@ -81,6 +81,10 @@ int pho_depth_sigma(int nscenes, int maxb, const int *n_bands, const int *wavele
                     int chain_mode, int max_intervals, double *table, int *n_intervals_out, double *trials,
                     float *depth_sigma);
 
+/* MODEL Lee_Kd_LS8 (mode 0) / Lee_Secchi_LS8 (mode 1), secchi.c:13-252; spv = nodata of the four planes */
+int pho_lee_ls8(int mode, int nrows, int ncols, const float *coastal, const float *blue, const float *green,
+                const float *red, const float *spv, float theta_s, float *out);
+
 #ifdef __cplusplus
 }
 #endif

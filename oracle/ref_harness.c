@@ -26,6 +26,11 @@
  * because that code is inlined in samodel() and cannot be called on its own.
  */
 #include "samodel.h"
+/* secchi.h has no include guard and only adds prototypes on top of common.h: declare what is driven */
+void Kd_LS8(float **coastal, float **blue, float **green, float **red, float **kd, int nrows, int ncols,
+            float coastal_spv, float blue_spv, float green_spv, float red_spv, float theta_s);
+void secchi_disk_depth(float **coastal, float **blue, float **green, float **red, float **zsd, int nrows, int ncols,
+                       float coastal_spv, float blue_spv, float green_spv, float red_spv, float theta_s);
 #if _OPENMP
 #include <omp.h>
 #endif
@@ -540,5 +545,25 @@ int ref_depth_sigma(int nscenes, int maxb, const int *n_bands, const int *wavele
   free(trial_depths); free(depth);
   for (g = 0; g < ngrids; g++) free(grids[g].array);
   free(grids); free(sc); free(scene_indexes);
+  return 0;
+}
+
+/*
+ * MODEL Lee_Kd_LS8 / Lee_Secchi_LS8 (bam.c:3250-3610): the reference's raster functions Kd_LS8 (secchi.c:13) and
+ * secchi_disk_depth (secchi.c:59) on four Landsat-8 reflectance planes. mode 0: Kd (minimum diffuse attenuation),
+ * mode 1: Secchi-disk depth. spv: the four planes' nodata values (coastal, blue, green, red).
+ */
+int ref_lee_ls8(int mode, int nrows, int ncols, const float *coastal, const float *blue, const float *green,
+                const float *red, const float *spv, float theta_s, float *out) {
+  float **p[5];
+  const float *src[5] = {coastal, blue, green, red, out};
+  int k, r;
+  for (k = 0; k < 5; k++) {
+    p[k] = (float **)malloc(nrows * sizeof(float *));
+    for (r = 0; r < nrows; r++) p[k][r] = (float *)(src[k] + (size_t)r * ncols);
+  }
+  if (mode == 0) Kd_LS8(p[0], p[1], p[2], p[3], p[4], nrows, ncols, spv[0], spv[1], spv[2], spv[3], theta_s);
+  else secchi_disk_depth(p[0], p[1], p[2], p[3], p[4], nrows, ncols, spv[0], spv[1], spv[2], spv[3], theta_s);
+  for (k = 0; k < 5; k++) free(p[k]);
   return 0;
 }

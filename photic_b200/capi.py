@@ -100,6 +100,9 @@ def lib() -> C.CDLL:
         L.phb_refine_host.argtypes = [C.c_void_p, _fp, C.c_float, _fp, C.c_float, _fp, C.c_float, C.c_int, C.c_int,
                                       C.c_int, _fp, _fp]
         L.phb_fp64_peak.argtypes = [C.c_void_p, _dp, _fp]
+        L.phb_lee_ls8_device.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, _fp, C.c_float,
+                                         C.c_int64, C.c_void_p, C.c_void_p]
+        L.phb_lee_ls8_host.argtypes = [C.c_void_p, C.c_int, _fp, _fp, _fp, _fp, _fp, C.c_float, C.c_int, C.c_int, _fp]
         L.phb_depth_sigma_host.argtypes = [C.c_void_p, C.POINTER(SceneDesc), C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p,
                                            C.c_uint, C.c_int, C.c_int, C.c_int, _fp, _dp, C.POINTER(C.c_int32), _dp,
                                            C.POINTER(Stats)]
@@ -110,7 +113,7 @@ def lib() -> C.CDLL:
 EXPORTS = ["phb_version", "phb_error_string", "phb_device_count", "phb_ctx_create", "phb_ctx_destroy",
            "phb_band_tables", "phb_invert_device", "phb_invert_host", "phb_debug_record_len", "phb_invert_host_debug",
            "phb_kat_objective", "phb_kat_math", "phb_refine_minmax_device", "phb_refine_device", "phb_refine_host",
-           "phb_fp64_peak", "phb_depth_sigma_host"]
+           "phb_fp64_peak", "phb_depth_sigma_host", "phb_lee_ls8_device", "phb_lee_ls8_host"]
 
 
 def check(rc: int) -> None:

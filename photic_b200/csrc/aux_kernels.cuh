@@ -62,8 +62,83 @@ __global__ void kat_math_kernel(int fn, const double *x, const double *y, long l
     else if (fn == 8) r = div_by_pi(x[i]);               /* against x / pi */
     else if (fn == 9) r = in_fast_range(x[i]) ? 1.0 : 0.0;
     else if (fn == 10) r = exp_arg_in_main_range(x[i]) ? 1.0 : 0.0;
-    else r = unit_range(x[i]) ? 1.0 : 0.0;               /* 11 */
+    else if (fn == 11) r = unit_range(x[i]) ? 1.0 : 0.0;
+    else r = phm::log10(x[i], tb.log_tab);               /* 12 */
     out[i] = r;
+  }
+}
+
+/* ---- MODEL Lee_Kd_LS8 / Lee_Secchi_LS8, model/secchi.c:13-252 ---------------------------------------
+ * Lee et al. (2016) QAA-style diffuse attenuation and Secchi-disk depth from the four Landsat-8 visible bands:
+ * closed form per cell, float in / float out, double arithmetic in between (secchi.c:117-252). log10 / pow /
+ * exp / log are the exact host-libm ports, the file is compiled without FMA contraction, so a cell equals the
+ * CPU's bit for bit. HBM-bound: 16 B in, 4 B out per cell. */
+struct LeeParams {
+  const float *coastal, *blue, *green, *red;
+  float *out;
+  long long n;
+  float spv[4];
+  float theta_s;
+  int mode; /* 0: Kd_LS8 (secchi.c:13), 1: secchi_disk_depth (secchi.c:59) */
+  const unsigned long long *exp_tab; const double *log_tab; const double *pow_tab;
+};
+
+__device__ __forceinline__ void lee_kd_bands(const float *Rrs, float theta_s, const phm::Tables &tb, float *kd) {
+  const double g0 = 0.0895, g1 = 0.1247, aw = 0.05866, h0 = -1.146, h1 = -1.366, h2 = 0.469;
+  const double bbw[4] = {0.00244761, 0.00171397, 0.000931339, 0.000448682};
+  const double ratio[4] = {554.0 / 443.0, 554.0 / 481.0, 1.0, 554.0 / 656.0};
+  const double m0 = 0.005, m1 = 4.26, m2 = 0.52, m3 = 10.8, gamma = 0.265;
+  double rrs[4], u[4], a[4], bb[4], bbp[4];
+#pragma unroll
+  for (int b = 0; b < 4; b++) {
+    rrs[b] = Rrs[b] / (0.52 + 1.7 * Rrs[b]);
+    u[b] = (-g0 + sqrt(g0 * g0 + 4.0 * g1 * rrs[b])) / (2.0 * g1);
+  }
+  const double chi = phm::log10((rrs[0] + rrs[1]) / (rrs[2] + 5.0 * rrs[3] * rrs[3] / rrs[1]), tb.log_tab);
+  a[2] = aw + phm::pow(10.0, h0 + h1 * chi + h2 * chi * chi, tb);
+  bb[2] = (-a[2] * g0 + 2.0 * a[2] * rrs[2] + a[2] * sqrt(g0 * g0 + 4.0 * g1 * rrs[2])) / (2.0 * (g0 + g1 - rrs[2]));
+  bbp[2] = (u[2] * a[2]) / (1 - u[2]) - bbw[2];
+  const double eta = 2.0 * (1.0 - 1.2 * phm::exp(-0.9 * rrs[0] / rrs[2], tb.exp_tab));
+#pragma unroll
+  for (int b = 0; b < 4; b++) {
+    if (b == 2) continue;
+    bbp[b] = bbp[2] * phm::pow(ratio[b], eta, tb);
+    a[b] = (1.0 - u[b]) * (bbw[b] + bbp[b]) / u[b];
+    bb[b] = (-a[b] * g0 + 2.0 * a[b] * rrs[b] + a[b] * sqrt(g0 * g0 + 4.0 * g1 * rrs[b])) / (2.0 * (g0 + g1 - rrs[b]));
+  }
+#pragma unroll
+  for (int b = 0; b < 4; b++) {
+    const double kk1 = (1.0 + m0 * theta_s) * a[b];
+    const double kk2 = m1 * (1.0 - gamma * bbw[b] / bb[b]);
+    const double kk3 = (1.0 - m2 * phm::exp(-m3 * a[b], tb.exp_tab)) * bb[b];
+    kd[b] = (float)(kk1 + kk2 * kk3);
+  }
+}
+
+__global__ void lee_ls8_kernel(const LeeParams p) {
+  phm::Tables tb;
+  tb.exp_tab = reinterpret_cast<const uint64_t *>(p.exp_tab);
+  tb.log_tab = p.log_tab;
+  tb.pow_tab = p.pow_tab;
+  for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < p.n; q += (long long)gridDim.x * blockDim.x) {
+    float R[4] = {__ldg(p.coastal + q), __ldg(p.blue + q), __ldg(p.green + q), __ldg(p.red + q)};
+    float res = p.spv[0];
+    if (R[0] != p.spv[0] && R[1] != p.spv[1] && R[2] != p.spv[2] && R[3] != p.spv[3]) {
+      float k4[4], kd[5];
+      lee_kd_bands(R, p.theta_s, tb, k4);
+      kd[0] = k4[0]; kd[1] = k4[1]; kd[2] = (float)(0.20 * k4[1] + 0.75 * k4[2]); kd[3] = k4[2]; kd[4] = k4[3]; /* secchi.c:45-49 */
+      float kmin = kd[0];
+#pragma unroll
+      for (int i = 0; i < 5; i++) if (kd[i] < kmin) kmin = kd[i]; /* vec_min, common.c:755 */
+      if (p.mode == 0) res = kmin;
+      else {
+        float mx = R[0];
+#pragma unroll
+        for (int i = 0; i < 4; i++) if (R[i] > mx) mx = R[i]; /* vec_max, common.c:797 */
+        res = (float)(phm::log(fabs(0.14 - mx) / 0.013, tb.log_tab) / (2.5 * kmin)); /* secchi.c:113 */
+      }
+    }
+    p.out[q] = res;
   }
 }
 

@@ -250,6 +250,36 @@ PHM_HD double log(double x, const double *T) {
   return log_core(ix, T);
 }
 
+/* ---- log10 ----------------------------------------------------------------------------- */
+
+/* __ieee754_log10 (glibc sysdeps/ieee754/dbl-64/e_log10.c, the fdlibm wrapper): the argument is split into
+ * 2^k and a mantissa in [1, 2) (or [0.5, 1) when k < 0), log() of the mantissa is the routine above, and the
+ * result is assembled with separately rounded products (this file of glibc has no FMA variant). */
+PHM_HD double log10(double x, const double *T) {
+  const double two54 = 1.80143985094819840000e+16, ivln10 = 4.34294481903251816668e-01,
+               log10_2hi = 3.01029995663611771306e-01, log10_2lo = 3.69423907715893078616e-13;
+  uint64_t ix = bits(x);
+  int32_t hx = (int32_t)(ix >> 32);
+  uint32_t lx = (uint32_t)ix;
+  int32_t k = 0;
+  if (hx < 0x00100000) { /* x < 2^-1022 */
+    if (((hx & 0x7fffffff) | lx) == 0) return from_bits(0xfff0000000000000ull); /* log10(+-0) = -inf */
+    if (hx < 0) return from_bits(0x7ff8000000000000ull);                        /* log10(-#) = NaN   */
+    k -= 54;
+    x = mul_(x, two54);
+    ix = bits(x);
+    hx = (int32_t)(ix >> 32);
+  }
+  if (hx >= 0x7ff00000) return add_(x, x);
+  k += (hx >> 20) - 1023;
+  const int32_t i = (int32_t)(((uint32_t)k & 0x80000000u) >> 31);
+  hx = (hx & 0x000fffff) | ((0x3ff - i) << 20);
+  const double y = (double)(k + i);
+  x = from_bits(((uint64_t)(uint32_t)hx << 32) | (bits(x) & 0xffffffffull));
+  const double z = add_(mul_(y, log10_2lo), mul_(ivln10, log(x, T)));
+  return add_(z, mul_(y, log10_2hi));
+}
+
 /* ---- pow ------------------------------------------------------------------------------- */
 
 /* checkint() of e_pow.c: 0 not an integer, 1 odd, 2 even */

@@ -699,7 +699,7 @@ int phb_kat_objective(phb_ctx *c, const phb_scene_desc *desc, int nb_active, int
 }
 
 int phb_kat_math(phb_ctx *c, int fn, const double *x, const double *y, int64_t n, double *out) {
-  if (!c || !x || !out || n <= 0 || fn < 0 || fn > 11 || ((fn == 2 || fn == 3 || fn == 5) && !y)) return PHB_EINVAL;
+  if (!c || !x || !out || n <= 0 || fn < 0 || fn > 12 || ((fn == 2 || fn == 3 || fn == 5) && !y)) return PHB_EINVAL;
   CK(cudaSetDevice(c->device));
   double *dx, *dy = nullptr, *dout;
   CK(cudaMalloc(&dx, n * 8)); CK(cudaMalloc(&dout, n * 8));
@@ -766,6 +766,37 @@ int phb_refine_host(phb_ctx *c, const float *h_in, float nodata, const float *h_
                              shallow_nodata, (int64_t)n, flags, args, mm, d_out, nullptr);
   if (rc) return rc;
   CK(cudaMemcpy(h_out, d_out, n * 4, cudaMemcpyDeviceToHost));
+  return PHB_OK;
+}
+
+/* ---- MODEL Lee_Kd_LS8 / Lee_Secchi_LS8 (secchi.c) --------------------------------------------------- */
+
+int phb_lee_ls8_device(phb_ctx *c, int mode, const float *d_coastal, const float *d_blue, const float *d_green,
+                       const float *d_red, const float *spv, float theta_s, int64_t n, float *d_out, void *stream) {
+  if (!c || !d_coastal || !d_blue || !d_green || !d_red || !spv || !d_out || n <= 0 || (mode != 0 && mode != 1)) return PHB_EINVAL;
+  CK(cudaSetDevice(c->device));
+  LeeParams lp;
+  lp.coastal = d_coastal; lp.blue = d_blue; lp.green = d_green; lp.red = d_red; lp.out = d_out; lp.n = (long long)n;
+  for (int k = 0; k < 4; k++) lp.spv[k] = spv[k];
+  lp.theta_s = theta_s; lp.mode = mode;
+  lp.exp_tab = c->d_exp_tab; lp.log_tab = c->d_log_tab; lp.pow_tab = c->d_pow_tab;
+  lee_ls8_kernel<<<c->n_sm * 8, 256, 0, (cudaStream_t)stream>>>(lp);
+  CK(cudaGetLastError());
+  return PHB_OK;
+}
+
+int phb_lee_ls8_host(phb_ctx *c, int mode, const float *h_coastal, const float *h_blue, const float *h_green,
+                     const float *h_red, const float *spv, float theta_s, int nrows, int ncols, float *h_out) {
+  if (!c || !h_coastal || !h_blue || !h_green || !h_red || !spv || !h_out || nrows < 1 || ncols < 1) return PHB_EINVAL;
+  CK(cudaSetDevice(c->device));
+  const size_t n = (size_t)nrows * ncols;
+  CK(c->outs.ensure(5 * n));
+  float *d = c->outs.p;
+  const float *src[4] = {h_coastal, h_blue, h_green, h_red};
+  for (int k = 0; k < 4; k++) CK(cudaMemcpy(d + k * n, src[k], n * 4, cudaMemcpyHostToDevice));
+  int rc = phb_lee_ls8_device(c, mode, d, d + n, d + 2 * n, d + 3 * n, spv, theta_s, (int64_t)n, d + 4 * n, nullptr);
+  if (rc) return rc;
+  CK(cudaMemcpy(h_out, d + 4 * n, n * 4, cudaMemcpyDeviceToHost));
   return PHB_OK;
 }
 

@@ -181,6 +181,27 @@ class Inverter:
         check(self.lib.phb_kat_math(self.ctx, fn, _np_ptr(x, capi._dp), yp, x.size, _np_ptr(out, capi._dp)))
         return out
 
+    def lee_ls8_host(self, mode: int, coastal, blue, green, red, spv, theta_s: float):
+        """MODEL Lee_Kd_LS8 (mode 0) / Lee_Secchi_LS8 (mode 1) on four host planes (secchi.c:13-252)."""
+        pl = [np.ascontiguousarray(a, dtype=np.float32) for a in (coastal, blue, green, red)]
+        out = np.zeros_like(pl[0])
+        sp = np.ascontiguousarray(spv, dtype=np.float32)
+        check(self.lib.phb_lee_ls8_host(self.ctx, mode, *[_np_ptr(a, capi._fp) for a in pl], _np_ptr(sp, capi._fp),
+                                        float(theta_s), out.shape[0], out.shape[1], _np_ptr(out, capi._fp)))
+        return out
+
+    def lee_ls8_device(self, mode: int, coastal, blue, green, red, spv, theta_s: float, out=None, stream=None):
+        """Same on torch CUDA tensors (float32, contiguous); returns the output tensor."""
+        import torch
+        out = torch.empty_like(coastal) if out is None else out
+        sp = np.ascontiguousarray(spv, dtype=np.float32)
+        s = torch.cuda.current_stream(coastal.device) if stream is None else stream
+        check(self.lib.phb_lee_ls8_device(self.ctx, mode, C.c_void_p(coastal.data_ptr()), C.c_void_p(blue.data_ptr()),
+                                          C.c_void_p(green.data_ptr()), C.c_void_p(red.data_ptr()), _np_ptr(sp, capi._fp),
+                                          float(theta_s), coastal.numel(), C.c_void_p(out.data_ptr()),
+                                          C.c_void_p(s.cuda_stream)))
+        return out
+
     def fp64_peak(self):
         t, ms = C.c_double(0), C.c_float(0)
         check(self.lib.phb_fp64_peak(self.ctx, C.byref(t), C.byref(ms)))

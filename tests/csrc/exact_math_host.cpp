@@ -41,6 +41,14 @@ long long phm_check_pow(const double *x, const double *y, long long n, long long
   }
   return bad;
 }
+long long phm_check_log10(const double *x, long long n, long long *first) {
+  long long bad = 0; *first = -1;
+  for (long long i = 0; i < n; i++) {
+    volatile double xi = x[i];
+    if (!same(phm::log10(xi, g_log_tab), ::log10(xi))) { if (!bad) *first = i; bad++; }
+  }
+  return bad;
+}
 double phm_host_exp(double x) { return phm::exp(x, g_exp_tab); }
 double phm_host_log(double x) { return phm::log(x, g_log_tab); }
 double phm_host_pow(double x, double y) { phm::Tables tb = {g_exp_tab, g_log_tab, g_pow_tab}; return phm::pow(x, y, tb); }

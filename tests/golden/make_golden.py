@@ -141,9 +141,33 @@ def make_depth_sigma():
         n_spatial=spec.n_spatial, n_bottoms=spec.n_bottoms, nodata=scene.NODATA, use_prior=True, **res)
 
 
+def make_lee_ls8():
+    """MODEL Lee_Kd_LS8 / Lee_Secchi_LS8 through the reference's Kd_LS8 / secchi_disk_depth (secchi.c)."""
+    build()
+    ref = Oracle("reference")
+    spec = scene.CONFIGS["murion"].scaled(96, 80)
+    planes, _ = scene.generate(spec)
+    c, b, g, r = [planes[k].numpy().copy() for k in range(4)]
+    rng = np.random.default_rng(20261018)
+    sl = slice(0, 24)  # free-ranging positive reflectances, incl. values the model turns into negative / huge Kd
+    for a, hi in ((c, 0.05), (b, 0.05), (g, 0.05), (r, 0.03)):
+        a[sl] = np.exp(rng.uniform(np.log(1e-6), np.log(hi), a[sl].shape)).astype(np.float32)
+    g[30, 5] = -9999.0  # nodata in one band only
+    spv = np.array([-9999.0, -9999.0, -9999.0, -9999.0], dtype=np.float32)
+    theta = 28.5
+    kd = ref.lee_ls8(0, c, b, g, r, spv, theta)
+    zsd = ref.lee_ls8(1, c, b, g, r, spv, theta)
+    print("lee_ls8: cells", kd.size, "valid", int((kd != -9999.0).sum()), "nan", int(np.isnan(kd).sum()), int(np.isnan(zsd).sum()))
+    np.savez_compressed(os.path.join(HERE, "lee_ls8.npz"), coastal=c, blue=b, green=g, red=r, spv=spv, theta_s=theta,
+                        kd=kd, zsd=zsd)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "depth_sigma":
         make_depth_sigma()
+    elif len(sys.argv) > 1 and sys.argv[1] == "lee_ls8":
+        make_lee_ls8()
     else:
         main()
         make_depth_sigma()
+        make_lee_ls8()

@@ -21,7 +21,7 @@ def host():
         os.makedirs(os.path.dirname(SO), exist_ok=True)
         subprocess.run(["g++", "-O2", "-mfma", "-ffp-contract=off", "-shared", "-fPIC", "-o", SO, SRC, "-lm"], check=True)
     lib = C.CDLL(SO)
-    for f in (lib.phm_check_exp, lib.phm_check_log, lib.phm_check_pow):
+    for f in (lib.phm_check_exp, lib.phm_check_log, lib.phm_check_pow, lib.phm_check_log10):
         f.restype = C.c_longlong
     return lib
 
@@ -65,6 +65,15 @@ def test_log(host):
     for x in (SPECIAL, rng.uniform(1e-6, 2, n), rng.uniform(0.9, 1.1, n), np.exp(rng.uniform(-700, 700, n)),
               rng.integers(0, 2**64, n, dtype=np.uint64).view(np.float64)):
         assert _bad1(host.phm_check_log, x) == (0, None)
+
+
+def test_log10(host):
+    """glibc's log10 (fdlibm wrapper around log; used by the Lee Kd / Secchi model, secchi.c:155)."""
+    rng = np.random.default_rng(4)
+    n = 2_000_000
+    for x in (SPECIAL, rng.uniform(1e-6, 20, n), rng.uniform(0.9, 1.1, n), np.exp(rng.uniform(-700, 700, n)),
+              rng.integers(0, 2**64, n, dtype=np.uint64).view(np.float64)):
+        assert _bad1(host.phm_check_log10, x) == (0, None)
 
 
 def test_pow(host):

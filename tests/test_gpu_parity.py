@@ -228,6 +228,27 @@ def test_depth_sigma_matches_reference(inverter, mode):
     assert np.array_equal(sig.view(np.int32), g[f"sigma{mode}"].view(np.int32))
 
 
+def test_lee_kd_secchi_match_reference(inverter):
+    """MODEL Lee_Kd_LS8 / Lee_Secchi_LS8 (secchi.c) on the GPU == the reference's rasters (golden), bit for bit,
+    through the host entry and the device entry."""
+    import torch
+    g = load_golden("lee_ls8")
+    for mode, key in ((0, "kd"), (1, "zsd")):
+        got = inverter.lee_ls8_host(mode, g["coastal"], g["blue"], g["green"], g["red"], g["spv"], float(g["theta_s"]))
+        same = (got.view(np.int32) == g[key].view(np.int32)) | (np.isnan(got) & np.isnan(g[key]))
+        assert same.all(), key
+        dev = [torch.from_numpy(g[k]).cuda() for k in ("coastal", "blue", "green", "red")]
+        got2 = inverter.lee_ls8_device(mode, *dev, g["spv"], float(g["theta_s"])).cpu().numpy()
+        assert np.array_equal(got2.view(np.int32), got.view(np.int32))
+
+
+def test_device_log10_equals_host_libm(inverter):
+    import math
+    rng = np.random.default_rng(6)
+    x = np.concatenate([np.exp(rng.uniform(-40, 40, 200_000)), rng.uniform(0.9, 1.1, 50_000), [1.0, 10.0, 1e-310, 0.5]])
+    assert bits_equal(inverter.kat_math(12, x), np.array([math.log10(v) for v in x])).all()
+
+
 def test_refine_matches_oracle(inverter, oracle_port):
     """REFINE (model/refine.c): every flag combination against the CPU restatement, bit exact."""
     from photic_b200 import capi

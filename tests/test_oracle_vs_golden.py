@@ -110,3 +110,13 @@ def test_depth_sigma_matches_reference_golden(oracle_port, mode):
     assert bits_equal(trials, g[f"trials{mode}"]).all()
     assert bits_equal(table, g[f"table{mode}"]).all()
     assert np.array_equal(sig.view(np.int32), g[f"sigma{mode}"].view(np.int32))
+
+
+def test_lee_kd_secchi_match_reference_golden(oracle_port):
+    """MODEL Lee_Kd_LS8 / Lee_Secchi_LS8 (secchi.c): restatement == the reference's rasters, bit for bit."""
+    g = load_golden("lee_ls8")
+    for mode, key in ((0, "kd"), (1, "zsd")):
+        got = oracle_port.lee_ls8(mode, g["coastal"], g["blue"], g["green"], g["red"], g["spv"], float(g["theta_s"]))
+        same = (got.view(np.int32) == g[key].view(np.int32)) | (np.isnan(got) & np.isnan(g[key]))
+        assert same.all(), key
+    assert (g["kd"] != -9999.0).sum() > 3000
