@@ -128,7 +128,7 @@ def cpu_baseline(spec, args, planes_np, prior_np, target_s, steps=1):
                       f"omp schedule(dynamic), gcc -O3, mean {out['n_evals'].mean():.0f} evals/px)"}, times, len(sel)
 
 
-def run_reference(args):
+def run_reference(args, emit=print):
     """--impl reference: the reference's own CPU implementation, all host threads, same workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -144,7 +144,7 @@ def run_reference(args):
     t = times[args.warmup:]
     val = npx * len(t) / float(np.sum(t))
     base["value"] = val
-    print(json.dumps({
+    emit(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(t)), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -170,8 +170,18 @@ def main():
     args = parse()
     if args.batches <= 0:
         args.batches = max(1, args.steps)
+    # stdout carries exactly ONE line, the JSON result: everything else that libraries print there (NCCL's
+    # "NCCL version ..." banner, OpenMP notices) is sent to stderr for the duration of the run.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line: str):
+        sys.stdout.flush()
+        os.write(real_stdout, (line + "\n").encode())
+
     if args.impl == "reference":
-        return run_reference(args)
+        return run_reference(args, emit)
 
     import torch
     import torch.distributed as dist
@@ -325,6 +335,12 @@ def main():
                       "smem_bytes": stats[0]["smem_bytes"], "regs": stats[0]["regs"]},
             "e2e": e2e, "gpu_launches": 3 * K * world, "clocks": clocks,
         }
+        # measured DRAM traffic of the kernel: bytes per pixel from the committed `ncu --set full` capture x pixels per launch
+        tpath = os.path.join(ROOT, "profiles", "r01_solve_kernel_traffic.json")
+        if os.path.exists(tpath):
+            tj = json.load(open(tpath))
+            line["roofline"]["traffic"] = tj["dram_bytes_per_pixel"] * total_px / (K * world)
+            line["roofline"]["traffic_source"] = "profiles/r01_solve_kernel_traffic.json (ncu dram__bytes_read+write per pixel) x pixels per launch"
         # algorithmic HBM traffic (reported, not binding): planes + prior in, 9 planes + flags out
         bytes_px = spec.n_planes * 4 + 4 + 9 * 4 + 5
         line["roofline"]["hbm_gbs_algorithmic"] = bytes_px * rb * spec.ncols * K * world / (total_ms * 1e-3) / 1e9
@@ -332,7 +348,7 @@ def main():
             p, pr = data[need[0]]
             base, _, _ = cpu_baseline(spec.scaled(rb, spec.ncols), args, p.cpu().numpy(), pr.cpu().numpy(), args.cpu_seconds)
             line["cpu_baseline"] = base
-        print(json.dumps(line))
+        emit(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
