@@ -143,6 +143,44 @@ def test_run_to_run_determinism_and_device_entry(inverter):
     assert st["n_valid"] == st_h["n_valid"] > 0 and st["alg_flops"] == st_h["alg_flops"] > 0
 
 
+def test_full_size_exmouth_sampled_against_oracle(inverter, oracle_port):
+    """BASELINE.json configs[1] at FULL size (3930x2858, 6 dates, ~6 M valid pixels) through the device entry:
+    size-independent properties (every valid pixel inverted exactly once, defaults elsewhere, flags consistent)
+    plus a random sample of pixels checked against the CPU oracle on the same full-size raster, bit for bit
+    at float32 output precision (what samodel() stores) and in the evaluation counts / convergence flags."""
+    import torch
+    from oracle.binding import SceneCfg
+    from photic_b200 import capi, scene
+    from photic_b200.samodel import Inverter
+    spec = scene.CONFIGS["exmouth"]
+    planes, prior = scene.generate(spec, device="cuda")
+    desc = capi.desc_from_spec(spec)
+    o = Inverter.alloc_device_outputs(desc, "cuda", scene_planes=False)
+    st = inverter.invert_device(desc, planes, prior, o)
+    torch.cuda.synchronize()
+    valid = scene.valid_mask(planes)
+    n_valid = int(valid.sum())
+    assert st["n_valid"] == n_valid > 5_000_000
+    depth = o["depth"]
+    assert bool((depth[valid] < 0).all()) and bool((depth[~valid] == 0).all())          # negated depth on valid pixels only
+    assert bool((o["bottom_type"][~valid] == -9999.0).all()) and bool((o["n_evals"][~valid] == 0).all())
+    assert bool((o["n_evals"][valid] > 100).all()) and int(o["converged"].sum()) == st["n_converged"]
+    assert st["n_converged"] > 0.999 * n_valid
+    idx = torch.nonzero(valid.reshape(-1)).reshape(-1)
+    g = torch.Generator().manual_seed(7)
+    pick = idx[torch.randperm(idx.numel(), generator=g)[:160].to(idx.device)].cpu().numpy()
+    ii, jj = pick // spec.ncols, pick % spec.ncols
+    ref = oracle_port.invert_pixels(SceneCfg.from_spec(spec), planes.cpu().numpy(), scene.NODATA, prior.cpu().numpy(),
+                                    scene.NODATA, ii, jj, nthreads=0)
+    got = {k: o[k].cpu().numpy()[ii, jj] for k in ("depth", "model_error", "K_min", "bottom_albedo", "index_optical_depth",
+                                                   "bottom_sand", "n_evals", "converged")}
+    rec = ref["rec"]
+    assert np.array_equal(got["depth"].view(np.int32), (-rec[:, 0].astype(np.float32)).view(np.int32))
+    for name, col in (("model_error", 1), ("bottom_albedo", 2), ("bottom_sand", 3), ("K_min", 6), ("index_optical_depth", 7)):
+        assert np.array_equal(got[name].view(np.int32), rec[:, col].astype(np.float32).view(np.int32)), name
+    assert np.array_equal(got["n_evals"], ref["n_evals"]) and np.array_equal(got["converged"], ref["converged"].astype(np.uint8))
+
+
 def test_objective_known_answers_on_device(inverter):
     """samodel_error / samodel_Rrs on random parameter vectors: reference's own outputs (golden)."""
     from photic_b200 import capi, scene
