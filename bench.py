@@ -219,7 +219,7 @@ def main():
             pr = torch.cat([pr, torch.full((rb - (r1 - r0), spec.ncols), scene.NODATA, device=dev)], dim=0).contiguous()
         data[b] = (p, pr)
         # estimated work per row: a shallow-water pixel (all substrates) costs ~3x a sand-only one
-        cost[b] = sharded.row_cost(scene.valid_mask(p), pr.abs() <= 8.0)
+        cost[b] = sharded.row_cost_from_prior(scene.valid_mask(p), pr)
     torch.cuda.synchronize()
     peak_tflops, _ = inv.fp64_peak()
     gather_names = capi.SCALAR_PLANES

@@ -51,6 +51,24 @@ def row_cost(valid: torch.Tensor, shallow: torch.Tensor, shallow_weight: float =
     return (v * (1.0 + (shallow_weight - 1.0) * shallow.to(torch.float32))).sum(dim=1)
 
 
+# Relative cost of one inversion as a function of the DEPTHS prior |h| (metres): mean evaluation count per depth
+# bin measured with the CPU oracle on Exmouth- and Pilbara-shaped rasters (1600 px each, tools notes in DESIGN.md
+# section 7) times the per-evaluation cost of the class (all substrates below 8 m: 1.3x a sand-only evaluation,
+# tools/class_cost.py). Normalised to the 8-12 m sand-only bin.
+_COST_EDGES = (2.0, 4.0, 6.0, 8.0, 12.0, 16.0, 24.0, 32.0)
+_COST_WEIGHT = (2.4, 2.9, 2.6, 2.2, 1.0, 1.1, 1.05, 1.35, 1.4)
+
+
+def row_cost_from_prior(valid: torch.Tensor, prior: torch.Tensor) -> torch.Tensor:
+    """Estimated work per row from the validity mask and the DEPTHS prior plane ([rows, cols]); a pixel whose
+    prior is above -1 m is inverted from 1 m (samodel.c:963-967)."""
+    h = prior.abs().clamp(min=1.0).to(torch.float32)
+    edges = torch.tensor(_COST_EDGES, dtype=torch.float32, device=prior.device)
+    wts = torch.tensor(_COST_WEIGHT, dtype=torch.float32, device=prior.device)
+    c = wts[torch.bucketize(h, edges, right=True)]
+    return (c * valid.to(torch.float32)).sum(dim=1)
+
+
 def exchange_halo(band: torch.Tensor, plan, halo: int, rank: int, world: int, group=None) -> torch.Tensor:
     """band: [planes, r1-r0, cols] rows owned by this rank. Returns the band with up to `halo` rows of the
     neighbouring bands attached above and below (fewer at the image edge). Empty bands are skipped over."""

@@ -52,7 +52,7 @@ wall0 = time.time()
 ev[0].record()
 # 1. cost estimate -> balanced bands
 cost = torch.zeros(spec.nrows, device=dev)
-cost[e0:e1] = sharded.row_cost(scene.valid_mask(planes_eq), prior_eq.abs() <= 8.0)
+cost[e0:e1] = sharded.row_cost_from_prior(scene.valid_mask(planes_eq), prior_eq)
 if world > 1:
     dist.all_reduce(cost)
 plan = sharded.plan_row_bands(cost.cpu().numpy(), world)
