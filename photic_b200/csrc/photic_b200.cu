@@ -236,9 +236,11 @@ int phb_ctx_create(int device, phb_ctx **out) {
   CK(cudaMalloc(&c->d_flops, sizeof(double)));
   for (int i = 0; i < 4; i++) CK(cudaEventCreate(&c->ev[i]));
   /* kHot[H_RCP_PI]: the refined reciprocal of pi exactly as this device's division fast path builds it */
-  rcp_pi_kernel<<<1, 1>>>(c->d_flops);
+  rcp_pi_kernel<<<1, 1>>>(reinterpret_cast<double *>(c->d_counters)); /* two doubles of scratch */
   CK(cudaGetLastError());
-  CK(cudaMemcpyToSymbol(kHot, c->d_flops, sizeof(double), H_RCP_PI * sizeof(double), cudaMemcpyDeviceToDevice));
+  CK(cudaMemcpyToSymbol(kHot, c->d_counters, sizeof(double), H_RCP_PI * sizeof(double), cudaMemcpyDeviceToDevice));
+  CK(cudaMemcpyToSymbol(kHot, reinterpret_cast<double *>(c->d_counters) + 1, sizeof(double), H_RCP_120 * sizeof(double),
+                        cudaMemcpyDeviceToDevice));
   CK(cudaDeviceSynchronize());
   *out = c;
   return PHB_OK;
@@ -699,7 +701,7 @@ int phb_kat_objective(phb_ctx *c, const phb_scene_desc *desc, int nb_active, int
 }
 
 int phb_kat_math(phb_ctx *c, int fn, const double *x, const double *y, int64_t n, double *out) {
-  if (!c || !x || !out || n <= 0 || fn < 0 || fn > 12 || ((fn == 2 || fn == 3 || fn == 5) && !y)) return PHB_EINVAL;
+  if (!c || !x || !out || n <= 0 || fn < 0 || fn > 14 || ((fn == 2 || fn == 3 || fn == 5 || fn == 13) && !y)) return PHB_EINVAL;
   CK(cudaSetDevice(c->device));
   double *dx, *dy = nullptr, *dout;
   CK(cudaMalloc(&dx, n * 8)); CK(cudaMalloc(&dout, n * 8));

@@ -232,6 +232,20 @@ def test_branch_free_div_sqrt_exp_equal_ieee_operators(inverter):
         assert bits_equal(inverter.kat_math(8, a), inverter.kat_math(5, a, pi)).all()
 
 
+def test_guarded_division_and_sqrt_equal_ieee_everywhere(inverter):
+    """div_by / sqrt_guarded (fast path inside its range, the ordinary operator outside) == a / b and sqrt(x) for ANY
+    operands: random bit patterns (NaN, inf, subnormals, zeros included) and the magnitudes the objective produces."""
+    rng = np.random.default_rng(12)
+    n = 2_000_000
+    special = np.array([0.0, -0.0, np.inf, -np.inf, np.nan, 5e-324, 2.2250738585072014e-308, 1.7976931348623157e308, 1.0, 120.0])
+    a = np.concatenate([rng.integers(0, 2 ** 64, n, dtype=np.uint64).view(np.float64), np.repeat(special, len(special)),
+                        np.exp(rng.uniform(-30, 30, n))])
+    b = np.concatenate([rng.integers(0, 2 ** 64, n, dtype=np.uint64).view(np.float64), np.tile(special, len(special)),
+                        rng.choice([9.0, 81.0, 45.0, 216.0, 120.0, 0.0123], n)])
+    assert bits_equal(inverter.kat_math(13, a, b), inverter.kat_math(5, a, b)).all()
+    assert bits_equal(inverter.kat_math(14, a), inverter.kat_math(6, a)).all()
+
+
 def test_range_predicates_of_the_hot_loop(inverter):
     """The guards of the branch-free term read the high word of a double as a float (two FSETP each);
     they must select exactly the sets the integer exponent tests define."""
