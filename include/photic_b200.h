@@ -164,7 +164,7 @@ int phb_invert_host_debug(phb_ctx *ctx, const phb_scene_desc *desc, const float 
  * parameter vectors, mirroring oracle/ref_harness.c:ref_error_kat) and of the exact libm port. */
 int phb_kat_objective(phb_ctx *ctx, const phb_scene_desc *desc, int n_bottoms_active, int n_regions, int origin,
                       const double *rrs_measured, int nparams, int nvec, const double *params, double *out6);
-int phb_kat_math(phb_ctx *ctx, int fn /*0 exp,1 log,2 pow,3 fast_div,4 fast_sqrt,5 a/b,6 sqrt,7 exp_main,8 x/pi fast,9-11 range predicates,12 log10,13 guarded a/b,14 guarded sqrt*/, const double *x,
+int phb_kat_math(phb_ctx *ctx, int fn /*0 exp,1 log,2 pow,3 fast_div,4 fast_sqrt,5 a/b,6 sqrt,7 exp_main,8 x/pi fast,9-11 range predicates,12 log10,13/15 guarded a/b,14 guarded sqrt*/, const double *x,
                  const double *y, int64_t n, double *out);
 
 /*

@@ -65,7 +65,8 @@ __global__ void kat_math_kernel(int fn, const double *x, const double *y, long l
     else if (fn == 11) r = unit_range(x[i]) ? 1.0 : 0.0;
     else if (fn == 12) r = phm::log10(x[i], tb.log_tab);
     else if (fn == 13) r = div_by(x[i], y[i], rcp_refined(y[i]), in_fast_range(y[i])); /* guarded division by a fixed divisor */
-    else r = sqrt_guarded(x[i]);                          /* 14 */
+    else if (fn == 14) r = sqrt_guarded(x[i]);
+    else r = div_guarded(x[i], y[i]);                     /* 15 */
     out[i] = r;
   }
 }

@@ -701,7 +701,7 @@ int phb_kat_objective(phb_ctx *c, const phb_scene_desc *desc, int nb_active, int
 }
 
 int phb_kat_math(phb_ctx *c, int fn, const double *x, const double *y, int64_t n, double *out) {
-  if (!c || !x || !out || n <= 0 || fn < 0 || fn > 14 || ((fn == 2 || fn == 3 || fn == 5 || fn == 13) && !y)) return PHB_EINVAL;
+  if (!c || !x || !out || n <= 0 || fn < 0 || fn > 15 || ((fn == 2 || fn == 3 || fn == 5 || fn == 13 || fn == 15) && !y)) return PHB_EINVAL;
   CK(cudaSetDevice(c->device));
   double *dx, *dy = nullptr, *dout;
   CK(cudaMalloc(&dx, n * 8)); CK(cudaMalloc(&dout, n * 8));

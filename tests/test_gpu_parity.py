@@ -243,6 +243,7 @@ def test_guarded_division_and_sqrt_equal_ieee_everywhere(inverter):
     b = np.concatenate([rng.integers(0, 2 ** 64, n, dtype=np.uint64).view(np.float64), np.tile(special, len(special)),
                         rng.choice([9.0, 81.0, 45.0, 216.0, 120.0, 0.0123], n)])
     assert bits_equal(inverter.kat_math(13, a, b), inverter.kat_math(5, a, b)).all()
+    assert bits_equal(inverter.kat_math(15, a, b), inverter.kat_math(5, a, b)).all()
     assert bits_equal(inverter.kat_math(14, a), inverter.kat_math(6, a)).all()
 
 
