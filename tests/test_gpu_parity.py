@@ -61,9 +61,11 @@ def test_golden_scenes_bit_exact(inverter, name):
     ("murion", 40, 31, {}), ("exmouth", 37, 29, {}), ("abudhabi", 24, 20, {}), ("qatar", 30, 30, {}),
     ("pilbara", 16, 33, {}), ("murion", 1, 23, {}), ("murion", 19, 1, {}), ("murion", 12, 12, {"n_spatial": 0}),
     ("exmouth", 12, 12, {"n_bottoms": 1}), ("murion", 10, 10, {"n_dates": 1}), ("murion", 10, 10, {"n_bottoms": 8}),
+    ("murion", 8, 8, {"n_dates": 9}),    # 36 (scene,band) slots: the SBP = 128 instantiations of the kernel
+    ("murion", 7, 7, {"n_dates": 16}),   # PHB_MAX_SCENES: n = 111 parameters, four coordinates per lane, T = 576
 ])
 def test_seeded_scenes_vs_oracle(inverter, oracle_port, cfg_name, R, C, over):
-    """Fresh seeded scenes (ragged shapes, single row / column, 1 date, 1 and 8 substrates, NSPATIAL 0)."""
+    """Fresh seeded scenes (ragged shapes, single row / column, 1 / 9 / 16 dates, 1 and 8 substrates, NSPATIAL 0)."""
     from oracle.binding import SceneCfg
     from photic_b200 import capi, scene
     spec = replace(scene.CONFIGS[cfg_name].scaled(R, C), **over)
