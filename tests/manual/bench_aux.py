@@ -5,11 +5,11 @@
   refine    REFINE kernel (CLIP|SCALE|POWER)          -> GB/s (4 B in + 4 B out per cell)
   sigma     depth-error estimate (samodel.c:1376-1477) -> trials/s in both chain modes
 each with the reference's CPU code timed beside it on a bounded sample (oracle/_ref when present, else the port).
-usage: python tools/bench_aux.py [--rows 3930 --cols 2858]
+usage: python tests/manual/bench_aux.py [--rows 3930 --cols 2858]
 """
 import argparse, json, os, sys, time
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import torch
 from photic_b200 import capi, scene

@@ -1,9 +1,9 @@
 #!/usr/bin/env python3
 """One whole BASELINE.json scene through the sharded path, timed end to end on the devices.
 
-    python tools/run_scene.py --config exmouth                                   (one GPU)
+    python tests/manual/run_scene.py --config exmouth                                   (one GPU)
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29531 \\
-        tools/run_scene.py --config pilbara [--refine]                            (8 GPUs)
+        tests/manual/run_scene.py --config pilbara [--refine]                            (8 GPUs)
 
 Every rank starts with an equal split of the scene's rows resident in HBM (synthetic, generated in place). Timed:
 cost estimate + all-reduce -> cost-balanced row bands -> rows re-dealt point-to-point (NCCL over NVLink) -> halo
@@ -12,7 +12,7 @@ nine result planes on rank 0. Rank 0 prints one JSON line (also written to gpuru
 """
 import argparse, json, os, sys, time
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import torch
 import torch.distributed as dist
