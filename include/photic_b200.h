@@ -39,7 +39,8 @@ enum {
   PHB_EINVAL = 1,    /* bad descriptor / argument                         */
   PHB_ENODEVICE = 2, /* no usable CUDA device (there is no CPU fallback)   */
   PHB_ECUDA = 3,     /* a CUDA call failed; see phb_error_string           */
-  PHB_ENOMEM = 4     /* host or device allocation failed                   */
+  PHB_ENOMEM = 4,    /* host or device allocation failed                   */
+  PHB_ENOFIT = 5     /* phb_jerlov_*: the reference's `return false` paths  */
 };
 
 /*
@@ -198,6 +199,26 @@ int phb_lee_ls8_device(phb_ctx *ctx, int mode, const float *d_coastal, const flo
                        const float *d_red, const float *spv, float theta_s, int64_t n, float *d_out, void *stream);
 int phb_lee_ls8_host(phb_ctx *ctx, int mode, const float *h_coastal, const float *h_blue, const float *h_green,
                      const float *h_red, const float *spv, float theta_s, int nrows, int ncols, float *h_out);
+
+/*
+ * COMPUTE K (bam.c:2362-2392 -> model/jerlov.c): Jerlov water type and spectral attenuation coefficients, the
+ * scene-level prior the K penalties of samodel_error are tuned around. HOST functions by design:
+ * a few hundred transect points in, a handful of scalars out, sequential FP64 regression sums (jerlov_host.h);
+ * no device and no phb_ctx needed. Bit-identical to the reference (tests/test_jerlov.py, golden from oracle/_ref).
+ *   phb_jerlov_fit          `jerlov` jerlov.c:75-210 (+ `linear_fit` common.c:418): out6 = K_i, K_j, slope m,
+ *                           intercept c, correlation r, fractional water-type index (0 = OI .. 9 = C9);
+ *                           PHB_ENOFIT where the reference returns false (outputs computed so far are kept,
+ *                           the others are 0). The reference's progress printf()s are not reproduced.
+ *   phb_jerlov_k            `compute_k` / `compute_k_from_jerlov` jerlov.c:274-316: K at each wavelength for a
+ *                           water-type index in [0, 9) (the reference reads past its table beyond that: PHB_EINVAL);
+ *                           0.0 for a wavelength outside 400..700 nm, as there.
+ *   phb_jerlov_k_from_ratio `compute_k_from_ratio` jerlov.c:214-270.
+ */
+int phb_jerlov_fit(float wlen_i, float wlen_j, float lsm_i, float lsm_j, const float *Li, const float *Lj, int npoints,
+                   float manual_ratio, float *out6, int32_t *n_shallow);
+int phb_jerlov_k(float water_type, const float *wavelengths, int n, float *k);
+int phb_jerlov_k_from_ratio(float ratio, float wlen_i, float wlen_j, const float *wavelengths, int n, float *water_type,
+                            float *k);
 
 /* FP64 pipe peak of this device, measured with a dependent-free DFMA chain kernel (MEASURED_PEAKS.json
  * has no FP64 entry). Returns TFLOP/s (2 flops per DFMA) and the kernel time. */

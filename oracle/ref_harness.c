@@ -567,3 +567,38 @@ int ref_lee_ls8(int mode, int nrows, int ncols, const float *coastal, const floa
   for (k = 0; k < 5; k++) free(p[k]);
   return 0;
 }
+
+/*
+ * COMPUTE K (bam.c:2362-2392): the reference's own jerlov.c (compiled where it lies), driven as bam.c drives it.
+ * Outputs are zeroed first: the reference leaves them untouched on its `return false` paths.
+ */
+bool jerlov(float wlen_i, float wlen_j, float Lsmi, float Lsmj, float *Li, float *Lj, int npoints, float *ki, float *kj,
+            float *m, float *c, float *r, float *water_type, float manual_ratio);
+float compute_k(float water_type, float wlen);
+void compute_k_from_jerlov(float water_type, float *alphas, int *spectral_indexes, float *wavelengths, int nspec);
+bool compute_k_from_ratio(float ratio, float wlen_i, float wlen_j, float *water_type, float *k, float *wavelengths,
+                          float n_wlens);
+
+int ref_jerlov_fit(float wlen_i, float wlen_j, float lsm_i, float lsm_j, const float *Li, const float *Lj, int npoints,
+                   float manual_ratio, float *out6) {
+  int k;
+  for (k = 0; k < 6; k++) out6[k] = 0.0f;
+  return jerlov(wlen_i, wlen_j, lsm_i, lsm_j, (float *)Li, (float *)Lj, npoints, &out6[0], &out6[1], &out6[2], &out6[3],
+                &out6[4], &out6[5], manual_ratio) ? 1 : 0;
+}
+
+void ref_jerlov_k(float water_type, const float *wavelengths, int n, float *k) {
+  /* through compute_k_from_jerlov with the identity index map, as bam.c:2379 calls it */
+  int i, *idx = (int *)malloc((n > 0 ? n : 1) * sizeof(int));
+  for (i = 0; i < n; i++) { idx[i] = i; k[i] = 0.0f; }
+  compute_k_from_jerlov(water_type, k, idx, (float *)wavelengths, n);
+  free(idx);
+}
+
+int ref_jerlov_k_from_ratio(float ratio, float wlen_i, float wlen_j, const float *wavelengths, int n, float *water_type,
+                            float *k) {
+  int i;
+  *water_type = 0.0f;
+  for (i = 0; i < n; i++) k[i] = 0.0f;
+  return compute_k_from_ratio(ratio, wlen_i, wlen_j, water_type, k, (float *)wavelengths, (float)n) ? 1 : 0;
+}

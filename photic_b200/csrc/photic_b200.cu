@@ -21,6 +21,7 @@
 #include "device_model.cuh"
 #include "invert_kernel.cuh"
 #include "aux_kernels.cuh"
+#include "jerlov_host.h"
 
 using namespace phb;
 
@@ -179,6 +180,7 @@ const char *phb_error_string(int code) {
     case PHB_ENODEVICE: return "no usable CUDA device (photic_b200 has no CPU fallback)";
     case PHB_ECUDA: return g_last_cuda_error.c_str();
     case PHB_ENOMEM: return "out of memory";
+    case PHB_ENOFIT: return "no Jerlov fit: singular regression or slope / wavelength outside Jerlov's table";
     default: return "unknown error";
   }
 }
@@ -828,6 +830,35 @@ int phb_fp64_peak(phb_ctx *c, double *tflops, float *ms) {
   if (ms) *ms = best;
   cudaFree(d_sink);
   return PHB_OK;
+}
+
+/* ---- Jerlov water type and spectral attenuation (jerlov.c; host-side scene constants, see jerlov_host.h) ---- */
+
+int phb_jerlov_fit(float wlen_i, float wlen_j, float lsm_i, float lsm_j, const float *Li, const float *Lj, int npoints,
+                   float manual_ratio, float *out6, int32_t *n_shallow) {
+  if (!out6 || npoints < 0 || (npoints > 0 && (!Li || !Lj))) return PHB_EINVAL;
+  phb_jerlov::Fit f;
+  memset(&f, 0, sizeof(f));
+  const bool ok = phb_jerlov::fit(wlen_i, wlen_j, lsm_i, lsm_j, Li, Lj, npoints, manual_ratio, &f);
+  out6[0] = f.ki; out6[1] = f.kj; out6[2] = f.m; out6[3] = f.c; out6[4] = f.r; out6[5] = f.water_type;
+  if (n_shallow) *n_shallow = f.n_shallow;
+  return ok ? PHB_OK : PHB_ENOFIT;
+}
+
+int phb_jerlov_k(float water_type, const float *wavelengths, int n, float *k) {
+  if (n < 0 || (n > 0 && (!wavelengths || !k))) return PHB_EINVAL;
+  int rc = PHB_OK;
+  for (int i = 0; i < n; i++)
+    if (!phb_jerlov::k_of_type(water_type, wavelengths[i], &k[i])) rc = PHB_EINVAL;
+  return rc;
+}
+
+int phb_jerlov_k_from_ratio(float ratio, float wlen_i, float wlen_j, const float *wavelengths, int n, float *water_type,
+                            float *k) {
+  if (!water_type || n < 0 || (n > 0 && (!wavelengths || !k))) return PHB_EINVAL;
+  *water_type = 0.0f;
+  for (int i = 0; i < n; i++) k[i] = 0.0f;
+  return phb_jerlov::k_from_ratio(ratio, wlen_i, wlen_j, wavelengths, n, water_type, k) ? PHB_OK : PHB_ENOFIT;
 }
 
 }  /* extern "C" */

@@ -162,12 +162,89 @@ def make_lee_ls8():
                         kd=kd, zsd=zsd)
 
 
+def make_jerlov():
+    """COMPUTE K through the reference's own jerlov.c (jerlov, compute_k_from_jerlov, compute_k_from_ratio)."""
+    import ctypes as C
+    from oracle.binding import REF_SO
+    build()
+    L = C.CDLL(REF_SO)
+    fp = C.POINTER(C.c_float)
+    L.ref_jerlov_fit.argtypes = [C.c_float] * 4 + [fp, fp, C.c_int, C.c_float, fp]
+    L.ref_jerlov_k.argtypes = [C.c_float, fp, C.c_int, fp]
+    L.ref_jerlov_k_from_ratio.argtypes = [C.c_float, C.c_float, C.c_float, fp, C.c_int, fp, fp]
+    P = lambda a: a.ctypes.data_as(fp)  # noqa: E731
+    rng = np.random.default_rng(20261019)
+    bands = np.array([443.0, 482.0, 561.0, 655.0], dtype=np.float32)
+    # the reference printf()s its progress: keep the generator's stdout readable
+    sys.stdout.flush()
+    saved = os.dup(1)
+    devnull = os.open(os.devnull, os.O_WRONLY)
+    os.dup2(devnull, 1)
+    try:
+        fits = []
+        for case in range(96):
+            bi, bj = rng.choice(4, 2, replace=False)
+            wi, wj = float(bands[bi]), float(bands[bj])
+            if case % 8 == 7:  # wavelengths off the band centres, incl. the table's ends
+                wi, wj = [float(v) for v in rng.choice([400.0, 425.0, 512.5, 699.0, 700.0, 450.0], 2, replace=False)]
+            npts = int(rng.integers(3, 400))
+            z = np.sort(rng.uniform(0.5, 25.0, npts))
+            ki_true, slope = rng.uniform(0.02, 0.5), rng.uniform(0.2, 6.0)
+            lsmi, lsmj = float(rng.uniform(5.0, 60.0)), float(rng.uniform(5.0, 60.0))
+            Li = (lsmi + rng.uniform(200, 4000) * np.exp(-2.0 * ki_true * z) * (1 + 0.03 * rng.standard_normal(npts))).astype(np.float32)
+            Lj = (lsmj + rng.uniform(200, 4000) * np.exp(-2.0 * ki_true * slope * z) * (1 + 0.03 * rng.standard_normal(npts))).astype(np.float32)
+            manual = 0.0
+            if case % 6 == 5:
+                manual = float(rng.uniform(0.3, 5.0))
+            if case == 10:  # every point below the deep-water signal: no shallow points, singular fit
+                Li[:] = lsmi
+            if case == 11:  # all points identical: singular fit
+                Li[:] = Li[0]
+                Lj[:] = Lj[0]
+            if case == 12:  # wavelength outside the table
+                wi = 380.0
+            out = np.zeros(6, dtype=np.float32)
+            ok = L.ref_jerlov_fit(wi, wj, lsmi, lsmj, P(Li), P(Lj), npts, manual, P(out))
+            fits.append((wi, wj, lsmi, lsmj, manual, Li, Lj, ok, out))
+        wts = np.concatenate([np.linspace(0.0, 8.999, 61), rng.uniform(0.0, 9.0, 67)]).astype(np.float32)
+        wls = np.concatenate([bands, [400.0, 700.0, 399.9, 700.1, 425.0, 512.3, 675.0, 0.0],
+                              rng.uniform(400.0, 700.0, 20)]).astype(np.float32)
+        kk = np.zeros((len(wts), len(wls)), dtype=np.float32)
+        for a, wt in enumerate(wts):
+            L.ref_jerlov_k(float(wt), P(wls), len(wls), P(kk[a]))
+        ratios = []
+        for case in range(64):
+            bi, bj = rng.choice(4, 2, replace=False)
+            ratio = float(np.float32(rng.uniform(0.05, 12.0)))
+            wt = C.c_float(0.0)
+            k = np.zeros(len(wls), dtype=np.float32)
+            ok = L.ref_jerlov_k_from_ratio(ratio, float(bands[bi]), float(bands[bj]), P(wls), len(wls), C.byref(wt), P(k))
+            ratios.append((ratio, float(bands[bi]), float(bands[bj]), ok, np.float32(wt.value), k))
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(devnull)
+    print("jerlov: fits ok", sum(f[7] for f in fits), "of", len(fits), "; ratio cases ok", sum(r[3] for r in ratios), "of", len(ratios))
+    lens = np.array([len(f[5]) for f in fits], dtype=np.int32)
+    np.savez_compressed(
+        os.path.join(HERE, "jerlov.npz"),
+        fit_args=np.array([f[:5] for f in fits], dtype=np.float32), fit_len=lens,
+        fit_Li=np.concatenate([f[5] for f in fits]), fit_Lj=np.concatenate([f[6] for f in fits]),
+        fit_ok=np.array([f[7] for f in fits], dtype=np.int32), fit_out=np.stack([f[8] for f in fits]),
+        k_wt=wts, k_wl=wls, k_out=kk,
+        ratio_args=np.array([r[:3] for r in ratios], dtype=np.float32), ratio_ok=np.array([r[3] for r in ratios], dtype=np.int32),
+        ratio_wt=np.array([r[4] for r in ratios], dtype=np.float32), ratio_k=np.stack([r[5] for r in ratios]))
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "depth_sigma":
         make_depth_sigma()
     elif len(sys.argv) > 1 and sys.argv[1] == "lee_ls8":
         make_lee_ls8()
+    elif len(sys.argv) > 1 and sys.argv[1] == "jerlov":
+        make_jerlov()
     else:
         main()
         make_depth_sigma()
         make_lee_ls8()
+        make_jerlov()
