@@ -128,6 +128,25 @@ int phb_invert_host(phb_ctx *ctx, const phb_scene_desc *desc, const float *const
                     int row_begin, int row_end, const phb_outputs *h_out, phb_stats *stats);
 
 /*
+ * One process, several GPUs: what the reference's OpenMP team is to its cores. The scene is cut into
+ * contiguous row bands of near-equal estimated cost (valid pixels weighted by the depth bin of their DEPTHS prior:
+ * shallow-water pixels carry all NBOTTOMS substrates and cost ~2.5x a sand-only one), each band is inverted by one
+ * context -- one per device -- on its own host thread, reading its rows plus (n_spatial-1)+(n_smoothing_radius-1)
+ * halo rows straight from the caller's host planes and writing its rows of the caller's output planes. Pixels are
+ * independent given the read-only halo, so there is no exchange between devices and the result equals
+ * phb_invert_host() on one device bit for bit.
+ *   ctxs      n_ctx contexts from phb_ctx_create (normally one per device; two on one device also work)
+ *   stats     sums over the bands, times = the slowest band; per_ctx (nullable) [n_ctx]; edges_out (nullable)
+ *             [n_ctx + 1]: band k = rows [edges[k], edges[k+1])
+ * phb_plan_row_bands is the planner on its own (host only, no device): edges [n_parts + 1], row_cost (nullable) [nrows].
+ */
+int phb_plan_row_bands(const phb_scene_desc *desc, const float *const *h_planes, const float *h_prior, int n_parts,
+                       int32_t *edges, double *row_cost);
+int phb_invert_host_multi(phb_ctx *const *ctxs, int n_ctx, const phb_scene_desc *desc, const float *const *h_planes,
+                          const float *h_prior, const phb_outputs *h_out, phb_stats *stats, phb_stats *per_ctx,
+                          int32_t *edges_out);
+
+/*
  * Depth-error estimate, the last phase of samodel() (samodel.c:1376-1477): for every 0.25 m depth interval
  * up to min(floor(max depth), 30 m), `n_samples` (128 in the reference) pixels are drawn at random inside the
  * interval (up to sqrt(nrows*ncols) probes each), re-inverted with every reflectance shifted by

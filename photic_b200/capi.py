@@ -106,6 +106,11 @@ def lib() -> C.CDLL:
         L.phb_depth_sigma_host.argtypes = [C.c_void_p, C.POINTER(SceneDesc), C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p,
                                            C.c_uint, C.c_int, C.c_int, C.c_int, _fp, _dp, C.POINTER(C.c_int32), _dp,
                                            C.POINTER(Stats)]
+        L.phb_plan_row_bands.argtypes = [C.POINTER(SceneDesc), C.POINTER(C.c_void_p), C.c_void_p, C.c_int,
+                                         C.POINTER(C.c_int32), _dp]
+        L.phb_invert_host_multi.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.POINTER(SceneDesc), C.POINTER(C.c_void_p),
+                                            C.c_void_p, C.POINTER(Outputs), C.POINTER(Stats), C.POINTER(Stats),
+                                            C.POINTER(C.c_int32)]
         L.phb_jerlov_fit.argtypes = [C.c_float, C.c_float, C.c_float, C.c_float, _fp, _fp, C.c_int, C.c_float, _fp,
                                      C.POINTER(C.c_int32)]
         L.phb_jerlov_k.argtypes = [C.c_float, _fp, C.c_int, _fp]
@@ -120,7 +125,8 @@ EXPORTS = ["phb_version", "phb_error_string", "phb_device_count", "phb_ctx_creat
            "phb_band_tables", "phb_invert_device", "phb_invert_host", "phb_debug_record_len", "phb_invert_host_debug",
            "phb_kat_objective", "phb_kat_math", "phb_refine_minmax_device", "phb_refine_device", "phb_refine_host",
            "phb_fp64_peak", "phb_depth_sigma_host", "phb_lee_ls8_device", "phb_lee_ls8_host",
-           "phb_jerlov_fit", "phb_jerlov_k", "phb_jerlov_k_from_ratio"]
+           "phb_jerlov_fit", "phb_jerlov_k", "phb_jerlov_k_from_ratio",
+           "phb_plan_row_bands", "phb_invert_host_multi"]
 
 
 def check(rc: int) -> None:

@@ -14,6 +14,7 @@
 #include <string.h>
 
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/photic_b200.h"
@@ -400,9 +401,13 @@ int phb_invert_device(phb_ctx *ctx, const phb_scene_desc *desc, const float *d_p
                             nullptr, nullptr, nullptr, 0);
 }
 
+/* Where the raster of `desc` sits inside the caller's host rasters: row `row0` of planes whose per-plane stride
+ * (for the stacked K / P / G / X outputs) is `plane_px` cells. {0, 0} = the host rasters ARE the raster of desc. */
+struct HostView { long long row0; size_t plane_px; };
+
 static int invert_host_impl(phb_ctx *c, const phb_scene_desc *desc, const float *const *h_planes, const float *h_prior,
                             int row_begin, int row_end, const phb_outputs *h_out, phb_stats *stats, double *rec,
-                            int32_t *pix, int32_t *iters, int64_t capacity) {
+                            int32_t *pix, int32_t *iters, int64_t capacity, HostView view = HostView{0, 0}) {
   if (!c || !h_planes || !h_out) return PHB_EINVAL;
   int rc = validate(desc);
   if (rc) return rc;
@@ -411,6 +416,8 @@ static int invert_host_impl(phb_ctx *c, const phb_scene_desc *desc, const float 
   int SB = 0, mb = 0;
   for (int s = 0; s < desc->n_scenes; s++) { SB += desc->n_bands[s]; mb = desc->n_bands[s] > mb ? desc->n_bands[s] : mb; }
   const size_t px = (size_t)desc->nrows * desc->ncols;
+  const size_t hpx = view.plane_px ? view.plane_px : px;          /* host stride of the stacked output planes */
+  const size_t h0 = (size_t)view.row0 * (size_t)desc->ncols;      /* first cell of this raster in the host planes */
   const int Ns = desc->n_scenes;
   cudaStream_t st = 0;
   cudaEvent_t e0, e1, e2, e3;
@@ -418,11 +425,11 @@ static int invert_host_impl(phb_ctx *c, const phb_scene_desc *desc, const float 
   CK(c->planes.ensure(px * SB));
   CK(cudaEventRecord(e0, st));
   for (int g = 0; g < SB; g++)
-    CK(cudaMemcpyAsync(c->planes.p + g * px, h_planes[g], px * sizeof(float), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(c->planes.p + g * px, h_planes[g] + h0, px * sizeof(float), cudaMemcpyHostToDevice, st));
   const bool use_prior = desc->prior_present && h_prior;
   if (use_prior) {
     CK(c->prior.ensure(px));
-    CK(cudaMemcpyAsync(c->prior.p, h_prior, px * sizeof(float), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(c->prior.p, h_prior + h0, px * sizeof(float), cudaMemcpyHostToDevice, st));
   }
   CK(cudaEventRecord(e1, st));
   /* device output planes: 9 scalar grids, K, P, G, X */
@@ -460,18 +467,18 @@ static int invert_host_impl(phb_ctx *c, const phb_scene_desc *desc, const float 
   const size_t a = (size_t)row_begin * desc->ncols, nb = (size_t)(row_end - row_begin) * desc->ncols;
   CK(cudaEventRecord(e2, st));
   for (int k = 0; k < 9; k++)
-    if (hslots[k]) CK(cudaMemcpyAsync(hslots[k] + a, *slots[k] + a, nb * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (hslots[k]) CK(cudaMemcpyAsync(hslots[k] + h0 + a, *slots[k] + a, nb * sizeof(float), cudaMemcpyDeviceToHost, st));
   if (h_out->K)
     for (int q = 0; q < Ns * mb; q++)
-      CK(cudaMemcpyAsync(h_out->K + q * px + a, d.K + q * px + a, nb * sizeof(float), cudaMemcpyDeviceToHost, st));
+      CK(cudaMemcpyAsync(h_out->K + q * hpx + h0 + a, d.K + q * px + a, nb * sizeof(float), cudaMemcpyDeviceToHost, st));
   float *const hpgx[3] = {h_out->P, h_out->G, h_out->X};
   float *const dpgx[3] = {d.P, d.G, d.X};
   for (int v = 0; v < 3; v++)
     if (hpgx[v])
       for (int s = 0; s < Ns; s++)
-        CK(cudaMemcpyAsync(hpgx[v] + s * px + a, dpgx[v] + s * px + a, nb * sizeof(float), cudaMemcpyDeviceToHost, st));
-  if (h_out->converged) CK(cudaMemcpyAsync(h_out->converged + a, c->conv.p + a, nb, cudaMemcpyDeviceToHost, st));
-  if (h_out->n_evals) CK(cudaMemcpyAsync(h_out->n_evals + a, c->nev.p + a, nb * sizeof(int), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(hpgx[v] + s * hpx + h0 + a, dpgx[v] + s * px + a, nb * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (h_out->converged) CK(cudaMemcpyAsync(h_out->converged + h0 + a, c->conv.p + a, nb, cudaMemcpyDeviceToHost, st));
+  if (h_out->n_evals) CK(cudaMemcpyAsync(h_out->n_evals + h0 + a, c->nev.p + a, nb * sizeof(int), cudaMemcpyDeviceToHost, st));
   if (d_rec) {
     CK(cudaMemcpyAsync(rec, d_rec, (size_t)capacity * reclen * sizeof(double), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(pix, d_pix, capacity * sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -495,6 +502,152 @@ int phb_invert_host_debug(phb_ctx *ctx, const phb_scene_desc *desc, const float 
                           int row_begin, int row_end, const phb_outputs *h_out, double *rec, int32_t *pix,
                           int32_t *n_iters, int64_t capacity, phb_stats *stats) {
   return invert_host_impl(ctx, desc, h_planes, h_prior, row_begin, row_end, h_out, stats, rec, pix, n_iters, capacity);
+}
+
+/* ---- one process, several GPUs: row bands over one context per device ----------------------- */
+
+namespace {
+
+/* Relative cost of one inversion by DEPTHS-prior bin: mean evaluation count per bin (CPU oracle, Exmouth- and
+ * Pilbara-shaped rasters) times the per-evaluation cost of the pixel class; the same table as
+ * photic_b200/sharded.py:row_cost_from_prior (8-band balance 0.77 -> 0.89 on Pilbara). */
+const float kCostEdges[8] = {2.0f, 4.0f, 6.0f, 8.0f, 12.0f, 16.0f, 24.0f, 32.0f};
+const float kCostWeight[9] = {2.4f, 2.9f, 2.6f, 2.2f, 1.0f, 1.1f, 1.05f, 1.35f, 1.4f};
+const float kCostNoPrior = 8.0f * 2.4f; /* eight H starts, all substrates (samodel.c:2222-2241) */
+
+/* estimated work of rows [r0, r1): validity as classify_kernel decides it (samodel.c:933-947), weight by prior bin */
+void row_costs(const phb_scene_desc *d, int SB, const float *const *planes, const float *prior, int r0, int r1,
+               double *cost) {
+  const int nc = d->ncols;
+  std::vector<unsigned char> ok(nc);
+  for (int r = r0; r < r1; r++) {
+    const size_t base = (size_t)r * nc;
+    for (int c = 0; c < nc; c++) ok[c] = 1;
+    for (int g = 0; g < SB; g++) {
+      const float *p = planes[g] + base;
+      for (int c = 0; c < nc; c++) {
+        const float v = p[c];
+        if (v < 0.0f || approx_equal_f(v, d->nodata, 1.0e-6f)) ok[c] = 0;
+      }
+    }
+    double acc = 0.0;
+    for (int c = 0; c < nc; c++) {
+      if (!ok[c]) continue;
+      float w = kCostNoPrior;
+      if (d->prior_present && prior) {
+        const float e = prior[base + c];
+        if (!approx_equal_f(e, d->prior_nodata, 1.0e-6f)) {
+          const float h = (e > -1.0f) ? 1.0f : fabsf(e);
+          int bin = 0;
+          while (bin < 8 && kCostEdges[bin] <= h) bin++;
+          w = kCostWeight[bin];
+        }
+      }
+      acc += (double)w;
+    }
+    cost[r] = acc;
+  }
+}
+
+/* contiguous bands of near-equal cumulative cost (photic_b200/sharded.py:plan_row_bands) */
+void plan_bands(const double *cost, int nrows, int parts, int32_t *edges) {
+  double total = 0.0;
+  for (int r = 0; r < nrows; r++) total += cost[r];
+  edges[0] = 0; edges[parts] = nrows;
+  if (!(total > 0.0)) {
+    for (int k = 1; k < parts; k++) edges[k] = (int32_t)llround((double)nrows * k / parts);
+    return;
+  }
+  double cum = 0.0;
+  int r = 0; /* edges[k] = smallest r with cost of rows [0, r) >= total * k / parts */
+  for (int k = 1; k < parts; k++) {
+    const double target = total * k / parts;
+    while (r < nrows && cum < target) cum += cost[r++];
+    edges[k] = r;
+  }
+}
+
+int scene_bands(const phb_scene_desc *d) {
+  int SB = 0;
+  for (int s = 0; s < d->n_scenes; s++) SB += d->n_bands[s];
+  return SB;
+}
+
+}  // namespace
+
+int phb_plan_row_bands(const phb_scene_desc *desc, const float *const *h_planes, const float *h_prior, int n_parts,
+                       int32_t *edges, double *row_cost) {
+  int rc = validate(desc);
+  if (rc) return rc;
+  if (!h_planes || !edges || n_parts < 1) return PHB_EINVAL;
+  const int SB = scene_bands(desc), nrows = desc->nrows;
+  std::vector<double> cost(nrows, 0.0);
+  int nthr = n_parts < nrows ? n_parts : nrows;
+  if (nthr > 16) nthr = 16;
+  std::vector<std::thread> th;
+  for (int t = 0; t < nthr; t++) {
+    const int r0 = (int)((long long)nrows * t / nthr), r1 = (int)((long long)nrows * (t + 1) / nthr);
+    th.emplace_back(row_costs, desc, SB, h_planes, h_prior, r0, r1, cost.data());
+  }
+  for (auto &t : th) t.join();
+  plan_bands(cost.data(), nrows, n_parts, edges);
+  if (row_cost) memcpy(row_cost, cost.data(), (size_t)nrows * sizeof(double));
+  return PHB_OK;
+}
+
+int phb_invert_host_multi(phb_ctx *const *ctxs, int n_ctx, const phb_scene_desc *desc, const float *const *h_planes,
+                          const float *h_prior, const phb_outputs *h_out, phb_stats *stats, phb_stats *per_ctx,
+                          int32_t *edges_out) {
+  if (!ctxs || n_ctx < 1 || n_ctx > 64 || !h_out) return PHB_EINVAL;
+  for (int k = 0; k < n_ctx; k++)
+    if (!ctxs[k]) return PHB_EINVAL;
+  std::vector<int32_t> edges(n_ctx + 1);
+  int rc = phb_plan_row_bands(desc, h_planes, h_prior, n_ctx, edges.data(), nullptr);
+  if (rc) return rc;
+  const int nrows = desc->nrows, SB = scene_bands(desc);
+  const int nsp = desc->n_spatial == 0 ? 1 : desc->n_spatial; /* samodel.c:2967 */
+  const int halo = (nsp - 1) + (desc->n_smoothing_radius - 1);
+  const size_t full_px = (size_t)nrows * desc->ncols;
+  std::vector<int> rcs(n_ctx, PHB_OK);
+  std::vector<std::string> errs(n_ctx);
+  std::vector<phb_stats> sts(n_ctx);
+  memset(sts.data(), 0, sizeof(phb_stats) * n_ctx);
+  auto work = [&](int k) {
+    const int r0 = edges[k], r1 = edges[k + 1];
+    if (r1 <= r0) return;
+    /* the band with its halo rows is a raster of its own: edge clamping then only ever happens at the real
+     * edges of the scene, so band + halo == unsharded (tests: row-band shards equal the whole scene) */
+    const int w0 = r0 - halo < 0 ? 0 : r0 - halo, w1 = r1 + halo > nrows ? nrows : r1 + halo;
+    phb_scene_desc dd = *desc;
+    dd.nrows = w1 - w0;
+    std::vector<const float *> pl(SB);
+    for (int g = 0; g < SB; g++) pl[g] = h_planes[g];
+    rcs[k] = invert_host_impl(ctxs[k], &dd, pl.data(), h_prior, r0 - w0, r1 - w0, h_out, &sts[k], nullptr, nullptr,
+                              nullptr, 0, HostView{w0, full_px});
+    if (rcs[k] == PHB_ECUDA) errs[k] = g_last_cuda_error;
+  };
+  std::vector<std::thread> th;
+  for (int k = 1; k < n_ctx; k++) th.emplace_back(work, k);
+  work(0);
+  for (auto &t : th) t.join();
+  for (int k = 0; k < n_ctx; k++)
+    if (rcs[k]) { if (rcs[k] == PHB_ECUDA) g_last_cuda_error = errs[k]; return rcs[k]; }
+  if (stats) {
+    memset(stats, 0, sizeof(*stats));
+    for (int k = 0; k < n_ctx; k++) {
+      const phb_stats &a = sts[k];
+      stats->n_valid += a.n_valid; stats->n_shallow += a.n_shallow; stats->n_evals += a.n_evals;
+      stats->n_iters += a.n_iters; stats->n_converged += a.n_converged; stats->alg_flops += a.alg_flops;
+      stats->ms_classify = a.ms_classify > stats->ms_classify ? a.ms_classify : stats->ms_classify;
+      stats->ms_solve = a.ms_solve > stats->ms_solve ? a.ms_solve : stats->ms_solve;
+      stats->ms_h2d = a.ms_h2d > stats->ms_h2d ? a.ms_h2d : stats->ms_h2d;
+      stats->ms_d2h = a.ms_d2h > stats->ms_d2h ? a.ms_d2h : stats->ms_d2h;
+      if (a.ctas) { stats->warps_per_cta = a.warps_per_cta; stats->ctas = a.ctas; stats->smem_bytes = a.smem_bytes; stats->regs = a.regs; }
+    }
+  }
+  if (per_ctx) memcpy(per_ctx, sts.data(), sizeof(phb_stats) * n_ctx);
+  if (edges_out) memcpy(edges_out, edges.data(), sizeof(int32_t) * (n_ctx + 1));
+  return PHB_OK;
 }
 
 

@@ -9,10 +9,12 @@
  * What it does, in the order samodel() does it:
  *   1. reads the scene fields samodel() reads (bands, int wavelengths, angles, tide: samodel.c:389-548)
  *   2. packs the float** row-pointer grids into contiguous planes (the device wants [plane][row][col])
- *   3. phb_invert_host(): validity scan, per-pixel cold-start inversion on the GPU, output defaults
+ *   3. phb_invert_host() -- or, with PHOTIC_B200_DEVICES=all|"0,1,..", phb_invert_host_multi(): cost-balanced
+ *      row bands over the GPUs of the box, one host thread per device inside this one process -- validity
+ *      scan, per-pixel cold-start inversion on the GPU, output defaults
  *   4. scatters the 9 result planes back into the caller's float** grids (depth already negated,
- *      samodel.c:1486-1490); depth_sigma is set to 0 (its Monte-Carlo pass is srand(time(NULL))-seeded
- *      in the reference and is row N1 of SURVEY.md 8f)
+ *      samodel.c:1486-1490); depth_sigma comes from phb_depth_sigma_host() (samodel.c:1376-1477; the
+ *      reference seeds it with time(NULL), here PHOTIC_B200_SIGMA_SEED can fix the seed)
  *   5. writes the per-scene K/P/G/X grids and the ten model grids through the host's write_nc, exactly
  *      the file names of samodel.c:1513-1687, when the host program provides write_nc
  * Errors: the reference has no error channel (printf + exit(1), common.h:62-67); so does this shim.
@@ -37,7 +39,49 @@ typedef bool photic_bool;
 extern void write_nc(char *file, float **grid, int ncols, int nrows, float *lons, float *lats, double spval)
     __attribute__((weak));
 
-static phb_ctx *g_ctx = NULL;
+static phb_ctx *g_ctx = NULL;             /* context of the first device (also runs the depth-error phase) */
+static phb_ctx *g_ctxs[64];
+static int g_n_ctx = 0;
+
+/* Devices: PHOTIC_B200_DEVICES=all | "0,2,5" (one row band per device, one process: phb_invert_host_multi),
+ * else PHOTIC_B200_DEVICE=<ordinal> (default 0). Contexts are created once and kept for the next MODEL command. */
+static void open_devices(void) {
+  const char *many = getenv("PHOTIC_B200_DEVICES"), *one = getenv("PHOTIC_B200_DEVICE");
+  int ids[64], n = 0, k, rc;
+  if (g_n_ctx > 0) return;
+  if (many && strcmp(many, "all") == 0) {
+    const int cnt = phb_device_count();
+    for (k = 0; k < cnt && k < 64; k++) ids[n++] = k;
+  } else if (many && *many) {
+    const char *p = many;
+    while (*p && n < 64) {
+      char *end;
+      const long v = strtol(p, &end, 10);
+      if (end == p) break;
+      ids[n++] = (int)v;
+      p = (*end == ',') ? end + 1 : end;
+    }
+  }
+  if (n == 0) ids[n++] = one ? atoi(one) : 0;
+  for (k = 0; k < n; k++) {
+    rc = phb_ctx_create(ids[k], &g_ctxs[k]);
+    if (rc) {
+      printf("\n\nERROR: photic_b200: cannot open CUDA device %d (there is no CPU fallback): %s\n\n", ids[k],
+             phb_error_string(rc));
+      exit(1);
+    }
+  }
+  g_n_ctx = n;
+  g_ctx = g_ctxs[0];
+}
+
+/* Releases the device contexts; the next samodel() call opens them again (and re-reads the environment). */
+void samodel_b200_shutdown(void) {
+  int k;
+  for (k = 0; k < g_n_ctx; k++) phb_ctx_destroy(g_ctxs[k]);
+  g_n_ctx = 0;
+  g_ctx = NULL;
+}
 
 static void die(const char *what, int rc) {
   printf("\n\nERROR: photic_b200: %s: %s\n\n", what, phb_error_string(rc));
@@ -127,15 +171,12 @@ void samodel(photic_scene scene_data[], photic_geogrid gridded_data[], int *scen
   if (!Kp || !Pp || !Gp || !Xp) { printf("\n\nERROR: Out of memory.\n\n"); exit(1); }
   out.K = Kp; out.P = Pp; out.G = Gp; out.X = Xp;
 
-  if (g_ctx == NULL) {
-    const char *dev = getenv("PHOTIC_B200_DEVICE");
-    rc = phb_ctx_create(dev ? atoi(dev) : 0, &g_ctx);
-    if (rc) die("cannot open a CUDA device (there is no CPU fallback)", rc);
-  }
-  rc = phb_invert_host(g_ctx, &d, planes, prior, 0, nrows, &out, &st);
+  open_devices();
+  if (g_n_ctx > 1) rc = phb_invert_host_multi(g_ctxs, g_n_ctx, &d, planes, prior, &out, &st, NULL, NULL);
+  else rc = phb_invert_host(g_ctx, &d, planes, prior, 0, nrows, &out, &st);
   if (rc) die("inversion failed", rc);
   printf("\nNumber of optically shallow pixels = %lld\n", (long long)st.n_valid);
-  printf("\nGPU inversion: %.1f ms (%.0f px/sec), mean iterations = %.0f, diverged = %.2f (%%)\n", st.ms_solve,
+  printf("\nGPU inversion on %d device(s): %.1f ms (%.0f px/sec), mean iterations = %.0f, diverged = %.2f (%%)\n", g_n_ctx, st.ms_solve,
          st.n_valid / (st.ms_solve * 1e-3 + 1e-12), st.n_valid ? (double)st.n_evals / st.n_valid : 0.0,
          st.n_valid ? 100.0 * (double)(st.n_valid - st.n_converged) / st.n_valid : 0.0);
 

@@ -104,6 +104,36 @@ class Inverter:
             out["rec_iters"] = (it[:n, 1] >> 1)[order]
         return out, st.as_dict()
 
+    @staticmethod
+    def plan_row_bands_host(desc: SceneDesc, planes, prior, n_parts: int):
+        """phb_plan_row_bands: cost-balanced contiguous row bands (host only, no device). Returns (edges, row_cost)."""
+        ptrs, keep = Inverter._plane_ptrs(planes)
+        pr = None if prior is None else np.ascontiguousarray(prior, dtype=np.float32)
+        edges = np.zeros(n_parts + 1, dtype=np.int32)
+        cost = np.zeros(desc.nrows, dtype=np.float64)
+        check(capi.lib().phb_plan_row_bands(C.byref(desc), ptrs, C.c_void_p(None) if pr is None else C.c_void_p(pr.ctypes.data),
+                                            n_parts, _np_ptr(edges, C.POINTER(C.c_int32)), _np_ptr(cost, capi._dp)))
+        return edges, cost
+
+    @staticmethod
+    def invert_host_multi(inverters, desc: SceneDesc, planes, prior, scene_planes=True, buffers=None):
+        """phb_invert_host_multi: one process, one Inverter (context) per device, cost-balanced row bands, one host
+        thread per band inside the library. Returns (outputs dict, stats dict incl. 'edges' and 'per_ctx')."""
+        n = len(inverters)
+        ptrs, keep = Inverter._plane_ptrs(planes)
+        pr = None if prior is None else np.ascontiguousarray(prior, dtype=np.float32)
+        o, out = inverters[0]._host_outputs(desc, scene_planes, buffers)
+        ctxs = (C.c_void_p * n)(*[iv.ctx.value for iv in inverters])
+        st, per = Stats(), (Stats * n)()
+        edges = np.zeros(n + 1, dtype=np.int32)
+        check(capi.lib().phb_invert_host_multi(ctxs, n, C.byref(desc), ptrs,
+                                               C.c_void_p(None) if pr is None else C.c_void_p(pr.ctypes.data), C.byref(o),
+                                               C.byref(st), per, _np_ptr(edges, C.POINTER(C.c_int32))))
+        d = st.as_dict()
+        d["edges"] = edges
+        d["per_ctx"] = [per[k].as_dict() for k in range(n)]
+        return out, d
+
     def depth_sigma_host(self, desc: SceneDesc, planes, prior, depth_neg, seed: int, n_samples: int = 128,
                          chain_mode: int = 1, max_intervals: int = 120):
         """Depth-error estimate of samodel() (samodel.c:1376-1477; phb_depth_sigma_host). ``depth_neg`` is the

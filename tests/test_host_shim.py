@@ -72,10 +72,16 @@ def test_shim_exports_reference_symbol(product_lib):
 
 
 @pytest.mark.gpu
-def test_shim_samodel_equals_library(inverter):
-    """Call the C samodel() the way bam.c:3236 does (row-pointer grids, geogrid by value)."""
+@pytest.mark.parametrize("devices", ["", "0,0,0"])
+def test_shim_samodel_equals_library(inverter, devices):
+    """Call the C samodel() the way bam.c:3236 does (row-pointer grids, geogrid by value); once on one device and
+    once through the in-process multi-device path (PHOTIC_B200_DEVICES: three row bands, here all on device 0)."""
     from photic_b200 import build, capi, scene
     lib = C.CDLL(build.build_host_shim())
+    lib.samodel_b200_shutdown()  # contexts are cached between calls: reopen under this test's environment
+    os.environ.pop("PHOTIC_B200_DEVICES", None)
+    if devices:
+        os.environ["PHOTIC_B200_DEVICES"] = devices
     spec = scene.CONFIGS["murion"].scaled(18, 14)
     planes, prior = scene.generate(spec)
     planes, prior = planes.numpy(), prior.numpy()
@@ -109,7 +115,11 @@ def test_shim_samodel_equals_library(inverter):
     lib.samodel.restype = None
     lib.samodel.argtypes = [C.POINTER(Scene), C.POINTER(Geogrid), C.POINTER(C.c_int), C.c_int, C.c_int, Geogrid, C.c_int,
                             C.c_int, C.c_int] + [C.POINTER(C.POINTER(C.c_float))] * 10 + [C.c_float, C.c_int, C.c_int]
-    lib.samodel(scenes, grids, idx, ns, 1, grids[spec.n_planes], 1, 2, 3, *[o[0] for o in outs], 8.0, 0, 1)
+    try:
+        lib.samodel(scenes, grids, idx, ns, 1, grids[spec.n_planes], 1, 2, 3, *[o[0] for o in outs], 8.0, 0, 1)
+    finally:
+        lib.samodel_b200_shutdown()
+        os.environ.pop("PHOTIC_B200_DEVICES", None)
     exp, st = inverter.invert_host(capi.desc_from_spec(spec), planes, prior)
     sigma, table, _, st2 = inverter.depth_sigma_host(capi.desc_from_spec(spec), planes, prior, exp["depth"], 77, 128, 1)
     order = ["depth", None, "model_error", "bottom_albedo", "bottom_sand", "bottom_seagrass", "bottom_coral", "K_min",
