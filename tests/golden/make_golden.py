@@ -162,6 +162,60 @@ def make_lee_ls8():
                         kd=kd, zsd=zsd)
 
 
+def extreme_params(rng, ns, nb, nr):
+    """Parameter vectors that leave the guaranteed range of the device's branch-free fast paths (exponent of exp
+    beyond +-512 or below 2^-54, huge / tiny / zero / non-finite operands) in some or all regions, so that the
+    out-of-line fallbacks run next to fast-path lanes. Layout: SURVEY.md appendix A.1."""
+    n = nr + 2 * nr * nb + 3 * ns
+    base = np.concatenate([rng.uniform(0.5, 30, nr), rng.uniform(5, 60, nr * nb), rng.uniform(0.1, 2, nr * nb),
+                           rng.uniform(0.5, 12, 3 * ns)])
+    off = nr + 2 * nr * nb
+    rows = []
+
+    def add(mod):
+        v = base.copy()
+        mod(v)
+        rows.append(v)
+
+    for h in (0.0, 1e-18, 1e-300, 95.0, 150.0, 300.0, 1e4, 1e300):
+        add(lambda v, h=h: v.__setitem__(slice(0, nr), h))          # every region
+        add(lambda v, h=h: v.__setitem__(slice(0, nr, 2), h))       # every other region: mixed lanes
+    for x in (1e8, 1e-30, 0.0, 1e300):
+        add(lambda v, x=x: v.__setitem__(slice(off + 2, n, 3), x))  # X (backscatter) of every scene
+        add(lambda v, x=x: v.__setitem__(off + 2, x))               # of the first scene only
+    for pv in (1e-10, 1e-300, 0.0, 1e6):
+        add(lambda v, pv=pv: v.__setitem__(slice(off, n, 3), pv))   # P
+        add(lambda v, pv=pv: v.__setitem__(slice(off + 1, n, 3), pv))  # G
+    for b in (1e5, 1e-300, 0.0, 1e300):
+        add(lambda v, b=b: v.__setitem__(slice(nr, nr + nr * nb), b))  # bottom albedo
+    add(lambda v: v.__setitem__(slice(nr + nr * nb, nr + nr * nb + nb), 0.0))  # q all zero in region 0: 0/0
+    add(lambda v: v.__setitem__(slice(nr + nr * nb, off), 1e-320))            # denormal mixing weights
+    add(lambda v: v.__setitem__(slice(0, n), 1e200))
+    add(lambda v: v.__setitem__(slice(0, n), -1e-200))
+    add(lambda v: v.__setitem__(0, float("inf")))
+    add(lambda v: v.__setitem__(1, float("nan")))
+    return np.array(rows)
+
+
+def make_kat_extreme():
+    """samodel_error of the UNMODIFIED reference on extreme parameter vectors (fallback paths of the device code)."""
+    build()
+    ref = Oracle("reference")
+    rng = np.random.default_rng(20261020)
+    kat = {}
+    for tag, ns, nb, nr in (("a", 6, 3, 9), ("b", 8, 1, 9), ("c", 4, 2, 4)):
+        spec = replace(scene.CONFIGS["murion"], n_dates=ns)
+        cfg = SceneCfg.from_spec(spec)
+        meas = rng.uniform(0.002, 0.02, (nr, ns, 4))
+        params = extreme_params(rng, ns, nb, nr)
+        origin = nr // 2
+        out, rrs, K = ref.error_kat(cfg, nb, nr, origin, meas, params)
+        print("kat_extreme", tag, params.shape, "finite objective in", int(np.isfinite(out[:, 0]).sum()), "of", len(out))
+        for k, v in (("meas", meas), ("params", params), ("out", out), ("meta", np.array([ns, nb, nr, origin]))):
+            kat[f"{tag}_{k}"] = v
+    np.savez_compressed(os.path.join(HERE, "kat_objective_extreme.npz"), **kat)
+
+
 def make_jerlov():
     """COMPUTE K through the reference's own jerlov.c (jerlov, compute_k_from_jerlov, compute_k_from_ratio)."""
     import ctypes as C
@@ -243,8 +297,11 @@ if __name__ == "__main__":
         make_lee_ls8()
     elif len(sys.argv) > 1 and sys.argv[1] == "jerlov":
         make_jerlov()
+    elif len(sys.argv) > 1 and sys.argv[1] == "kat_extreme":
+        make_kat_extreme()
     else:
         main()
         make_depth_sigma()
         make_lee_ls8()
         make_jerlov()
+        make_kat_extreme()

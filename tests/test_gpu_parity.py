@@ -194,6 +194,20 @@ def test_objective_known_answers_on_device(inverter):
         assert bits_equal(got, k[f"{tag}_out"]).all(), tag
 
 
+def test_objective_extreme_parameters_take_the_fallback_paths(inverter):
+    """Parameter vectors outside the guaranteed range of the branch-free division / sqrt / exp (H = 0, 1e-300, 150 m,
+    1e300; zero, tiny and huge IOPs and albedos; 0/0 mixing weights; inf and NaN coordinates), in all or only some
+    regions so that fallback lanes sit next to fast-path lanes: still the reference's bits, NaNs where it has NaNs."""
+    from photic_b200 import capi, scene
+    k = load_golden("kat_objective_extreme")
+    for tag in "abc":
+        ns, nb, nr, origin = (int(v) for v in k[f"{tag}_meta"])
+        spec = replace(scene.CONFIGS["murion"], n_dates=ns)
+        got = inverter.kat_objective(capi.desc_from_spec(spec), nb, nr, origin, k[f"{tag}_meas"], k[f"{tag}_params"])
+        eq = bits_equal(got, k[f"{tag}_out"])
+        assert eq.all(), (tag, np.argwhere(~eq)[:8], got[~eq][:8], k[f"{tag}_out"][~eq][:8])
+
+
 def test_device_math_equals_host_libm(inverter):
     """exp/log/pow on the device == the libm the reference links (same process, math module / numpy ufunc free)."""
     import math

@@ -35,6 +35,22 @@ def test_objective_known_answers(oracle_port):
         assert bits_equal(K, k[f"{tag}_K"]).all()
 
 
+def test_objective_known_answers_extreme_parameters(oracle_port):
+    """samodel_error where operands leave every comfortable range (H = 0 / 1e300, zero or huge IOPs, 0/0 mixing
+    weights, inf / NaN coordinates): the reference's own outputs, NaNs included."""
+    from oracle.binding import SceneCfg
+    from photic_b200 import scene
+    from dataclasses import replace
+    k = load_golden("kat_objective_extreme")
+    for tag in "abc":
+        ns, nb, nr, origin = (int(v) for v in k[f"{tag}_meta"])
+        cfg = SceneCfg.from_spec(replace(scene.CONFIGS["murion"], n_dates=ns))
+        out, _, _ = oracle_port.error_kat(cfg, nb, nr, origin, k[f"{tag}_meas"], k[f"{tag}_params"])
+        eq = bits_equal(out, k[f"{tag}_out"])
+        assert eq.all(), (tag, np.argwhere(~eq)[:5])
+        assert np.isnan(k[f"{tag}_out"][:, 0]).any() and np.isfinite(k[f"{tag}_out"][:, 0]).sum() > 30
+
+
 def test_nelmin_known_answers(oracle_port):
     k = load_golden("kat_nelmin")
     n_cases = len(k.files) // 2
