@@ -420,8 +420,12 @@ static int invert_host_impl(phb_ctx *c, const phb_scene_desc *desc, const float 
   const size_t h0 = (size_t)view.row0 * (size_t)desc->ncols;      /* first cell of this raster in the host planes */
   const int Ns = desc->n_scenes;
   cudaStream_t st = 0;
-  cudaEvent_t e0, e1, e2, e3;
-  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1)); CK(cudaEventCreate(&e2)); CK(cudaEventCreate(&e3));
+  struct Events { /* released on every return path */
+    cudaEvent_t e[4] = {nullptr, nullptr, nullptr, nullptr};
+    ~Events() { for (cudaEvent_t x : e) if (x) cudaEventDestroy(x); }
+  } evs;
+  for (int k = 0; k < 4; k++) CK(cudaEventCreate(&evs.e[k]));
+  const cudaEvent_t e0 = evs.e[0], e1 = evs.e[1], e2 = evs.e[2], e3 = evs.e[3];
   CK(c->planes.ensure(px * SB));
   CK(cudaEventRecord(e0, st));
   for (int g = 0; g < SB; g++)
@@ -488,7 +492,6 @@ static int invert_host_impl(phb_ctx *c, const phb_scene_desc *desc, const float 
   CK(cudaStreamSynchronize(st));
   CK(cudaEventElapsedTime(&local.ms_h2d, e0, e1));
   CK(cudaEventElapsedTime(&local.ms_d2h, e2, e3));
-  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); cudaEventDestroy(e3);
   if (stats) *stats = local;
   return PHB_OK;
 }

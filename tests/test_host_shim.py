@@ -71,6 +71,26 @@ def test_shim_exports_reference_symbol(product_lib):
     assert hasattr(lib, "samodel")
 
 
+def test_c_program_linking_the_drop_in_fails_loudly_without_a_device(product_lib, tmp_path):
+    """A C caller built like the reference's REPL (tests/csrc/mini_model.c) linked against the drop-in: on a machine
+    without a CUDA device samodel() must print the error and exit(1) -- the reference's own failure convention
+    (common.h:62-67) -- and never compute anything on the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present: the no-device path cannot be observed")
+    from photic_b200 import build
+    so = build.build_host_shim()
+    exe = str(tmp_path / "mini_model")
+    subprocess.run(["gcc", "-O1", "-Wall", "-I", os.path.join(ROOT, "photic_b200", "host"),
+                    os.path.join(ROOT, "tests", "csrc", "mini_model.c"), "-o", exe, "-L", os.path.dirname(so),
+                    "-lsamodel_b200", "-Wl,-rpath," + os.path.dirname(so)], check=True)
+    for env_extra in ({}, {"PHOTIC_B200_DEVICES": "all"}, {"PHOTIC_B200_DEVICES": "0,1"}):
+        r = subprocess.run([exe], capture_output=True, text=True, env={**os.environ, **env_extra}, timeout=120)
+        assert r.returncode == 1, (env_extra, r.returncode, r.stdout[-400:], r.stderr[-400:])
+        assert "ERROR: photic_b200" in r.stdout and "no CPU fallback" in r.stdout
+        assert "mini_model: depth" not in r.stdout
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("devices", ["", "0,0,0"])
 def test_shim_samodel_equals_library(inverter, devices):
