@@ -585,8 +585,11 @@ int phb_plan_row_bands(const phb_scene_desc *desc, const float *const *h_planes,
   if (!h_planes || !edges || n_parts < 1) return PHB_EINVAL;
   const int SB = scene_bands(desc), nrows = desc->nrows;
   std::vector<double> cost(nrows, 0.0);
-  int nthr = n_parts < nrows ? n_parts : nrows;
-  if (nthr > 16) nthr = 16;
+  int nthr = (int)std::thread::hardware_concurrency(); /* the scan is memory-bound host work: use the cores */
+  if (nthr < n_parts) nthr = n_parts;
+  if (nthr > 32) nthr = 32;
+  if (nthr > nrows) nthr = nrows;
+  if (nthr < 1) nthr = 1;
   std::vector<std::thread> th;
   for (int t = 0; t < nthr; t++) {
     const int r0 = (int)((long long)nrows * t / nthr), r1 = (int)((long long)nrows * (t + 1) / nthr);
