@@ -180,6 +180,11 @@ int phb_invert_host_debug(phb_ctx *ctx, const phb_scene_desc *desc, const float 
                           const float *h_prior, int row_begin, int row_end, const phb_outputs *h_out,
                           double *rec, int32_t *pix, int32_t *n_iters, int64_t capacity, phb_stats *stats);
 
+/* Test hook (host only): the scene-level constants block the kernels receive (struct ModelConst of
+ * csrc/device_model.cuh), for the CPU emulation of the solve kernel in tests/emu. Returns the block's size in
+ * bytes (-1 for a bad descriptor); fills `out` when capacity suffices. */
+int64_t phb_debug_model_const(const phb_scene_desc *desc, void *out, int64_t capacity);
+
 /* Known-answer hooks (device evaluation of the forward model / objective on caller-supplied
  * parameter vectors, mirroring oracle/ref_harness.c:ref_error_kat) and of the exact libm port. */
 int phb_kat_objective(phb_ctx *ctx, const phb_scene_desc *desc, int n_bottoms_active, int n_regions, int origin,

@@ -111,6 +111,8 @@ def lib() -> C.CDLL:
         L.phb_invert_host_multi.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.POINTER(SceneDesc), C.POINTER(C.c_void_p),
                                             C.c_void_p, C.POINTER(Outputs), C.POINTER(Stats), C.POINTER(Stats),
                                             C.POINTER(C.c_int32)]
+        L.phb_debug_model_const.argtypes = [C.POINTER(SceneDesc), C.c_void_p, C.c_int64]
+        L.phb_debug_model_const.restype = C.c_int64
         L.phb_jerlov_fit.argtypes = [C.c_float, C.c_float, C.c_float, C.c_float, _fp, _fp, C.c_int, C.c_float, _fp,
                                      C.POINTER(C.c_int32)]
         L.phb_jerlov_k.argtypes = [C.c_float, _fp, C.c_int, _fp]
@@ -126,7 +128,7 @@ EXPORTS = ["phb_version", "phb_error_string", "phb_device_count", "phb_ctx_creat
            "phb_kat_objective", "phb_kat_math", "phb_refine_minmax_device", "phb_refine_device", "phb_refine_host",
            "phb_fp64_peak", "phb_depth_sigma_host", "phb_lee_ls8_device", "phb_lee_ls8_host",
            "phb_jerlov_fit", "phb_jerlov_k", "phb_jerlov_k_from_ratio",
-           "phb_plan_row_bands", "phb_invert_host_multi"]
+           "phb_plan_row_bands", "phb_invert_host_multi", "phb_debug_model_const"]
 
 
 def check(rc: int) -> None:

@@ -212,6 +212,13 @@ int phb_band_tables(const phb_scene_desc *desc, double *out_tables, double *out_
   return PHB_OK;
 }
 
+/* test hook: the scene constants exactly as the kernels receive them (ModelConst, csrc/device_model.cuh), host only */
+int64_t phb_debug_model_const(const phb_scene_desc *desc, void *out, int64_t capacity) {
+  if (validate(desc) != PHB_OK) return -1;
+  if (out && capacity >= (int64_t)sizeof(ModelConst)) build_model(desc, static_cast<ModelConst *>(out));
+  return (int64_t)sizeof(ModelConst);
+}
+
 int phb_ctx_create(int device, phb_ctx **out) {
   if (!out) return PHB_EINVAL;
   int n = 0;

@@ -1,0 +1,80 @@
+"""The product's solve_kernel SOURCE run on the CPU (tests/emu: g++ build of photic_b200/csrc/invert_kernel.cuh, one
+warp = 32 fibers) against the CPU oracle: every retrieved parameter, evaluation count and convergence flag must be bit
+identical. Covers what can be wrong in the kernel's LOGIC without a GPU -- optimiser state machine, the simplex tiers
+(global slab with centroid checkpoints / shared memory), ordered sums, penalties, neighbourhood gather at raster
+edges, derived outputs and stores, the compile-time variants -- on every CPU run of the suite. What only a device can
+show (PTX fast paths, tensor memory, nvcc's code) stays with the `-m gpu` tests."""
+import os
+import sys
+from dataclasses import replace
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu"))
+from runner import Emulator  # noqa: E402
+
+from conftest import bits_equal  # noqa: E402
+
+
+def _case(cfg_name, R, C, over, n_pix, stride_seed=0):
+    from oracle.binding import SceneCfg
+    from photic_b200 import capi, scene
+    spec = replace(scene.CONFIGS[cfg_name].scaled(R, C), **over)
+    planes, prior = scene.generate(spec)
+    valid = scene.valid_mask(planes).numpy()
+    ii, jj = np.nonzero(valid)
+    step = max(1, len(ii) // n_pix)
+    sel = np.arange(stride_seed % step, len(ii), step)[:n_pix]
+    return spec, planes.numpy(), prior.numpy(), ii[sel], jj[sel], capi, scene, SceneCfg
+
+
+def _check(emu, oracle_port, cfg_name, R, C, over, n_pix, smem, use_prior=True):
+    spec, pl, pr, pi, pj, capi, scene, SceneCfg = _case(cfg_name, R, C, over, n_pix)
+    desc = capi.desc_from_spec(spec, prior_present=use_prior)
+    got = emu.invert_pixels(desc, pl, pr if use_prior else None, pi, pj, simplex_smem_bytes=smem)
+    ref = oracle_port.invert_pixels(SceneCfg.from_spec(spec), pl, scene.NODATA, pr if use_prior else None, scene.NODATA, pi, pj)
+    assert len(pi) >= min(2, n_pix)
+    assert np.array_equal(got["n_evals"], ref["n_evals"]), (got["n_evals"], ref["n_evals"])
+    assert np.array_equal(got["converged"], ref["converged"])
+    eq = bits_equal(got["rec"], ref["rec"])
+    assert eq.all(), np.argwhere(~eq)[:6]
+    # the float planes are what samodel() leaves: depth negated, Rrs error in model_error (samodel.c:1120-1160, 1486)
+    rec = ref["rec"]
+    assert np.array_equal(got["planes"][0][pi, pj].view(np.int32), (-rec[:, 0].astype(np.float32)).view(np.int32))
+    assert np.array_equal(got["planes"][1][pi, pj].view(np.int32), rec[:, 1].astype(np.float32).view(np.int32))
+    assert np.array_equal(got["n_evals_plane"][pi, pj], ref["n_evals"])
+    assert int(got["counters"][3]) == len(pi) and int(got["counters"][2]) == int(ref["converged"].sum())
+    return got
+
+
+@pytest.fixture(scope="module")
+def emu(product_lib):
+    return Emulator()
+
+
+@pytest.mark.parametrize("cfg_name,R,C,over,n_pix,smem", [
+    ("murion", 10, 8, {}, 10, 4096),                       # 4 dates, edges and corners of the raster (Nr = 4, 6, 9)
+    ("exmouth", 12, 10, {}, 6, 0),                         # 6 dates, the whole simplex in the global slab (checkpoints)
+    ("exmouth", 12, 10, {}, 4, 1 << 20),                   # the whole simplex in shared memory
+    ("abudhabi", 9, 9, {}, 3, 20000),                      # 8 dates: 32 (scene, band) slots exactly
+    ("qatar", 12, 12, {}, 4, 8192),                        # noisy mixed deep / shallow pixels
+    ("murion", 9, 8, {"n_spatial": 1}, 4, 2048),           # one region
+    ("murion", 8, 8, {"n_spatial": 3, "n_dates": 2}, 2, 30000),   # 25 regions
+    ("murion", 9, 8, {"n_smoothing_radius": 2, "n_bottoms": 2}, 3, 4096),  # box smoothing, run-time substrate count
+    ("murion", 8, 8, {"n_dates": 10}, 1, 16384),           # 40 (scene, band) slots: the 128-slot table stride
+])
+def test_emulated_kernel_equals_oracle(emu, oracle_port, cfg_name, R, C, over, n_pix, smem):
+    _check(emu, oracle_port, cfg_name, R, C, over, n_pix, smem)
+
+
+def test_emulated_kernel_without_depth_prior(emu, oracle_port):
+    """No DEPTHS grid: up to eight H starts per pixel with the early exit of samodel.c:2404."""
+    _check(emu, oracle_port, "murion", 8, 8, {}, 2, 4096, use_prior=False)
+
+
+@pytest.mark.parametrize("define", ["PHB_PIPELINE_TERMS=1", "PHB_COLD_OUT=1"])
+def test_emulated_variants_equal_oracle(product_lib, oracle_port, define):
+    """The off-by-default experiment switches of the kernel are the same arithmetic in another order."""
+    e = Emulator((define,), tag=define.split("=")[0].lower())
+    _check(e, oracle_port, "exmouth", 12, 10, {}, 3, 6000)
