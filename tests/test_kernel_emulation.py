@@ -63,6 +63,11 @@ def emu(product_lib):
     ("murion", 8, 8, {"n_spatial": 3, "n_dates": 2}, 2, 30000),   # 25 regions
     ("murion", 9, 8, {"n_smoothing_radius": 2, "n_bottoms": 2}, 3, 4096),  # box smoothing, run-time substrate count
     ("murion", 8, 8, {"n_dates": 10}, 1, 16384),           # 40 (scene, band) slots: the 128-slot table stride
+    ("murion", 8, 8, {"n_dates": 16}, 1, 30000),           # the maximum number of dates: 111 parameters, 4 per lane
+    ("murion", 9, 9, {"n_spatial": 3, "n_dates": 8}, 1, 60000),   # 25 regions x 8 dates: 199 parameters, 800 terms
+    ("murion", 8, 8, {"n_bottoms": 8, "n_dates": 3}, 1, 30000),   # every substrate of the table
+    ("murion", 8, 8, {"n_bottoms": 1}, 2, 3000),           # sand only everywhere
+    ("murion", 8, 8, {"n_dates": 1}, 3, 3000),             # a single date
 ])
 def test_emulated_kernel_equals_oracle(emu, oracle_port, cfg_name, R, C, over, n_pix, smem):
     _check(emu, oracle_port, cfg_name, R, C, over, n_pix, smem)
