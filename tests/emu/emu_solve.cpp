@@ -30,9 +30,46 @@ int g_cur = 0;
 void (*g_kernel)(const phb::SolveParams) = nullptr;
 const phb::SolveParams *g_params = nullptr;
 
+void (*g_body)() = nullptr; /* what every lane runs */
+
 void lane_entry() {
-  g_kernel(*g_params);
+  g_body();
   g_done[g_cur] = true; /* returns to g_main through uc_link */
+}
+void body_solve() { g_kernel(*g_params); }
+
+/* known answers of the objective: the body of kat_objective_kernel (csrc/aux_kernels.cuh) on the emulated warp */
+struct KatArgs { int nb_active, n_regions, origin, nvec; const double *meas, *params; double *out6; } g_kat;
+template <int SBP>
+void kat_objective_body() {
+  using namespace phb;
+  const SolveParams &p = *g_params;
+  const ModelConst &M = *p.M;
+  stage_cta(p, M, phb_smem);
+  __syncthreads();
+  Warp w;
+  const int lane = threadIdx.x & 31, SB = p.L.SB, Ns = p.L.Ns;
+  bind_warp(w, p, phb_smem, 0, 0);
+  Pixel px;
+  px.Nr = g_kat.n_regions; px.Nb = g_kat.nb_active; px.origin = g_kat.origin;
+  size_pixel(px, lane, SB, Ns, p.L.simplex_doubles, 0);
+  for (int t = lane; t < px.T; t += 32) w.meas[t] = g_kat.meas[t];
+  __syncwarp();
+  phm::Tables tb;
+  tb.exp_tab = w.exp_tab; tb.log_tab = p.log_tab; tb.pow_tab = p.pow_tab;
+  double Bs, Ps, Xs;
+  derive_pixel_constants(w, px, M, tb, lane, SB, Ns, Bs, Ps, Xs);
+  Side side;
+  for (int v = 0; v < g_kat.nvec; v++) {
+    for (int i = lane; i < px.n; i += 32) w.xmin[i] = g_kat.params[(size_t)v * px.n + i];
+    __syncwarp();
+    const double e = objective<0, SBP, true>(w, px, lane, SB, Ns, p.L.NbMax, w.xmin, side);
+    if (lane == 0) {
+      double *o = g_kat.out6 + (size_t)v * 6;
+      o[0] = e; o[1] = side.e_rrs; o[2] = side.e_depth; o[3] = side.e_bottom; o[4] = side.e_K; o[5] = side.bottom_albedo;
+    }
+    __syncwarp();
+  }
 }
 
 /* runs one warp to completion: every pass advances each live lane to its next collective */
@@ -122,9 +159,34 @@ int emu_invert(const void *model, int64_t model_size, const float *planes, const
   if (sp.L.SBP == 32) g_kernel = M.n_bottoms == 3 ? solve_kernel<3, 32, false> : solve_kernel<0, 32, false>;
   else g_kernel = M.n_bottoms == 3 ? solve_kernel<3, kMaxSB, false> : solve_kernel<0, kMaxSB, false>;
   g_params = &sp;
+  g_body = body_solve;
   run_warp();
   if (counters) memcpy(counters, cnt, sizeof(cnt));
   if (flops) *flops = fl;
+  return 0;
+}
+
+/* samodel_error on caller-supplied parameter vectors (what phb_kat_objective does on the device): out6 per vector =
+ * objective, Rrs error, depth / bottom / K penalties, bottom albedo */
+int emu_kat_objective(const void *model, int64_t model_size, int nb_active, int n_regions, int origin, const double *meas,
+                      int nvec, const double *params, double *out6) {
+  using namespace phb;
+  if (model_size != (int64_t)sizeof(ModelConst)) return 1;
+  const ModelConst &M = *static_cast<const ModelConst *>(model);
+  SolveParams sp;
+  memset(&sp, 0, sizeof(sp));
+  sp.L = make_layout(M.SB, M.n_scenes, M.n_bottoms, n_regions);
+  if ((size_t)sp.L.cta_bytes + (size_t)sp.L.warp_bytes > sizeof(phb_smem)) return 2;
+  memset(phb_smem, 0xcd, sizeof(phb_smem));
+  const long long slab_doubles = (long long)(sp.L.nmax + 1) * sp.L.nmax + sp.L.nmax + sp.L.Tmax + (long long)((sp.L.nmax + 8) / 8 + 1) * sp.L.nmax;
+  std::vector<double> slab(slab_doubles, 0.0);
+  sp.M = &M;
+  sp.slabs = slab.data(); sp.slab_stride = slab_doubles;
+  sp.exp_tab = reinterpret_cast<const unsigned long long *>(kExpTab); sp.log_tab = kLogTab; sp.pow_tab = kPowTab;
+  g_kat = KatArgs{nb_active, n_regions, origin, nvec, meas, params, out6};
+  g_params = &sp;
+  g_body = sp.L.SBP == 32 ? kat_objective_body<32> : kat_objective_body<kMaxSB>;
+  run_warp();
   return 0;
 }
 

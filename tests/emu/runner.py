@@ -62,3 +62,19 @@ class Emulator:
         assert np.array_equal(pix, q)
         return {"rec": rec, "n_evals": it[:, 0], "converged": it[:, 1] & 1, "n_iters": it[:, 1] >> 1, "planes": out9,
                 "converged_plane": conv, "n_evals_plane": nev, "counters": cnt, "alg_flops": fl.value}
+
+    def kat_objective(self, desc, nb_active, n_regions, origin, meas, params):
+        """samodel_error on parameter vectors (contract of Inverter.kat_objective / Oracle.error_kat's first output)."""
+        from photic_b200 import capi
+        L = capi.lib()
+        n = L.phb_debug_model_const(C.byref(desc), None, 0)
+        model = (C.c_ubyte * n)()
+        assert L.phb_debug_model_const(C.byref(desc), model, n) == n == self.lib.emu_model_const_size()
+        meas = np.ascontiguousarray(meas, dtype=np.float64)
+        params = np.ascontiguousarray(params, dtype=np.float64)
+        out = np.zeros((params.shape[0], 6))
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+        rc = self.lib.emu_kat_objective(model, C.c_int64(n), int(nb_active), int(n_regions), int(origin), vp(meas),
+                                        params.shape[0], vp(params), vp(out))
+        assert rc == 0, rc
+        return out

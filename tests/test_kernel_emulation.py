@@ -78,6 +78,23 @@ def test_emulated_kernel_without_depth_prior(emu, oracle_port):
     _check(emu, oracle_port, "murion", 8, 8, {}, 2, 4096, use_prior=False)
 
 
+@pytest.mark.parametrize("define", ["", "PHB_PIPELINE_TERMS=1", "PHB_COLD_OUT=1"])
+def test_emulated_objective_known_answers(product_lib, define):
+    """samodel_error of the kernel source on the reference's own known answers (tests/golden/kat_objective*.npz),
+    including the extreme parameter vectors that send lanes through the out-of-range fallbacks."""
+    from conftest import load_golden
+    from photic_b200 import capi, scene
+    e = Emulator((define,), tag=define.split("=")[0].lower()) if define else Emulator()
+    for gname, tags in (("kat_objective", "abcd"), ("kat_objective_extreme", "abc")):
+        k = load_golden(gname)
+        for tag in tags:
+            ns, nb, nr, origin = (int(v) for v in k[f"{tag}_meta"])
+            spec = replace(scene.CONFIGS["murion"], n_dates=ns)
+            got = e.kat_objective(capi.desc_from_spec(spec), nb, nr, origin, k[f"{tag}_meas"], k[f"{tag}_params"])
+            eq = bits_equal(got, k[f"{tag}_out"])
+            assert eq.all(), (gname, tag, np.argwhere(~eq)[:6])
+
+
 @pytest.mark.parametrize("define", ["PHB_PIPELINE_TERMS=1", "PHB_COLD_OUT=1"])
 def test_emulated_variants_equal_oracle(product_lib, oracle_port, define):
     """The off-by-default experiment switches of the kernel are the same arithmetic in another order."""
