@@ -24,19 +24,104 @@ namespace phb { __attribute__((aligned(16))) unsigned char phb_smem[256 * 1024];
 namespace {
 
 constexpr size_t kStack = 1u << 20;
-ucontext_t g_main, g_lane[32];
 bool g_done[32];
 int g_cur = 0;
 void (*g_kernel)(const phb::SolveParams) = nullptr;
 const phb::SolveParams *g_params = nullptr;
-
 void (*g_body)() = nullptr; /* what every lane runs */
 
+/* Fiber switch. glibc's swapcontext makes a sigprocmask system call per switch (two thirds of the emulation's run
+ * time); on x86-64 a dozen instructions do: callee-saved registers, MXCSR and the x87 control word, stack pointer. */
+#if defined(__x86_64__) && !defined(EMU_UCONTEXT)
+extern "C" void emu_switch(void **save_sp, void *load_sp);
+asm(R"(
+.text
+.globl emu_switch
+.type emu_switch,@function
+emu_switch:
+    pushq %rbp
+    pushq %rbx
+    pushq %r12
+    pushq %r13
+    pushq %r14
+    pushq %r15
+    subq $8, %rsp
+    stmxcsr (%rsp)
+    fnstcw 4(%rsp)
+    movq %rsp, (%rdi)
+    movq %rsi, %rsp
+    ldmxcsr (%rsp)
+    fldcw 4(%rsp)
+    addq $8, %rsp
+    popq %r15
+    popq %r14
+    popq %r13
+    popq %r12
+    popq %rbx
+    popq %rbp
+    ret
+.size emu_switch,.-emu_switch
+)");
+void *g_main_sp = nullptr, *g_lane_sp[32];
+void yield_to_main() { emu_switch(&g_lane_sp[g_cur], g_main_sp); }
+void resume_lane(int l) { emu_switch(&g_main_sp, g_lane_sp[l]); }
+extern "C" void emu_lane_trampoline() {
+  g_body();
+  g_done[g_cur] = true;
+  yield_to_main();
+  abort(); /* a finished lane is never resumed */
+}
+void make_lane(int l, char *stack) {
+  /* frame emu_switch pops: [mxcsr | x87 cw][r15 r14 r13 r12 rbx rbp][return address]; entry with rsp % 16 == 8 */
+  uintptr_t top = ((uintptr_t)stack + kStack) & ~(uintptr_t)15;
+  uint64_t *sp = reinterpret_cast<uint64_t *>(top) - 9;
+  uint32_t csr; uint16_t cw;
+  asm volatile("stmxcsr %0" : "=m"(csr));
+  asm volatile("fnstcw %0" : "=m"(cw));
+  sp[0] = (uint64_t)csr | ((uint64_t)cw << 32);
+  for (int k = 1; k <= 6; k++) sp[k] = 0;
+  sp[7] = (uint64_t)(uintptr_t)&emu_lane_trampoline;
+  sp[8] = 0;
+  g_lane_sp[l] = sp;
+}
+#else
+ucontext_t g_main, g_lane[32];
+void yield_to_main() { swapcontext(&g_lane[g_cur], &g_main); }
+void resume_lane(int l) { swapcontext(&g_main, &g_lane[l]); }
 void lane_entry() {
   g_body();
   g_done[g_cur] = true; /* returns to g_main through uc_link */
 }
+void make_lane(int l, char *stack) {
+  getcontext(&g_lane[l]);
+  g_lane[l].uc_stack.ss_sp = stack;
+  g_lane[l].uc_stack.ss_size = kStack;
+  g_lane[l].uc_link = &g_main;
+  makecontext(&g_lane[l], lane_entry, 0);
+}
+#endif
+
 void body_solve() { g_kernel(*g_params); }
+
+/* runs one warp to completion: every pass advances each live lane to its next collective */
+void run_warp() {
+  std::vector<char> stacks(32 * kStack + 64);
+  for (int l = 0; l < 32; l++) {
+    make_lane(l, stacks.data() + (size_t)l * kStack);
+    g_done[l] = false;
+  }
+  for (;;) {
+    int live = 0;
+    for (int l = 0; l < 32; l++) {
+      if (g_done[l]) continue;
+      live++;
+      g_cur = l;
+      threadIdx.x = (unsigned)l;
+      resume_lane(l);
+    }
+    if (live == 0) break;
+  }
+}
 
 /* known answers of the objective: the body of kat_objective_kernel (csrc/aux_kernels.cuh) on the emulated warp */
 struct KatArgs { int nb_active, n_regions, origin, nvec; const double *meas, *params; double *out6; } g_kat;
@@ -72,37 +157,13 @@ void kat_objective_body() {
   }
 }
 
-/* runs one warp to completion: every pass advances each live lane to its next collective */
-void run_warp() {
-  std::vector<char> stacks(32 * kStack);
-  for (int l = 0; l < 32; l++) {
-    getcontext(&g_lane[l]);
-    g_lane[l].uc_stack.ss_sp = stacks.data() + (size_t)l * kStack;
-    g_lane[l].uc_stack.ss_size = kStack;
-    g_lane[l].uc_link = &g_main;
-    makecontext(&g_lane[l], lane_entry, 0);
-    g_done[l] = false;
-  }
-  for (;;) {
-    int live = 0;
-    for (int l = 0; l < 32; l++) {
-      if (g_done[l]) continue;
-      live++;
-      g_cur = l;
-      threadIdx.x = (unsigned)l;
-      swapcontext(&g_main, &g_lane[l]);
-    }
-    if (live == 0) break;
-  }
-}
-
 const uint64_t kExpTab[2 * PHM_N] = PHM_EXP_TAB;
 const double kLogTab[2 * PHM_N] = PHM_LOG_TAB;
 const double kPowTab[3 * PHM_N] = PHM_POWLOG_TAB;
 
 }  // namespace
 
-void emu_warp_arrive() { swapcontext(&g_lane[g_cur], &g_main); }
+void emu_warp_arrive() { yield_to_main(); }
 
 extern "C" {
 
@@ -163,6 +224,72 @@ int emu_invert(const void *model, int64_t model_size, const float *planes, const
   run_warp();
   if (counters) memcpy(counters, cnt, sizeof(cnt));
   if (flops) *flops = fl;
+  return 0;
+}
+
+/*
+ * The whole device side of phb_invert_device on a small raster: classify_kernel (validity, defaults, the two
+ * work lists), concat_queue_kernel, solve_kernel. The two pre-pass kernels have no warp collectives and run as one
+ * thread; rows [row_begin, row_end). out: the nine planes [9][nrows][ncols]; K [Ns][max_bands][px], P/G/X [Ns][px]
+ * (nullable); records for the queued pixels in queue order (capacity = the row window's pixel count).
+ */
+int emu_invert_raster(const void *model, int64_t model_size, const float *planes, const float *prior, int row_begin,
+                      int row_end, int simplex_smem_bytes, float *out9, float *K, float *P, float *G, float *X,
+                      unsigned char *converged, int *n_evals, double *rec, int *pix, int *iters, int *n_valid,
+                      int *n_shallow) {
+  using namespace phb;
+  if (model_size != (int64_t)sizeof(ModelConst)) return 1;
+  const ModelConst &M = *static_cast<const ModelConst *>(model);
+  const size_t px = (size_t)M.nrows * M.ncols, win = (size_t)(row_end - row_begin) * M.ncols;
+  std::vector<int> q_shallow(win), q_deep(win), queue(win);
+  int scal[4] = {0, 0, 0, 0};
+  phb_outputs o;
+  memset(&o, 0, sizeof(o));
+  o.depth = out9; o.model_error = out9 + px; o.bottom_albedo = out9 + 2 * px; o.bottom_sand = out9 + 3 * px;
+  o.bottom_seagrass = out9 + 4 * px; o.bottom_coral = out9 + 5 * px; o.K_min = out9 + 6 * px; o.bottom_type = out9 + 7 * px;
+  o.index_optical_depth = out9 + 8 * px;
+  o.K = K; o.P = P; o.G = G; o.X = X; o.converged = converged; o.n_evals = n_evals;
+  ClassifyParams cp;
+  cp.M = &M; cp.planes = planes; cp.prior = M.prior_present ? prior : nullptr;
+  cp.row_begin = row_begin; cp.row_end = row_end;
+  cp.queue_shallow = q_shallow.data(); cp.queue_deep = q_deep.data(); cp.n_shallow = &scal[0]; cp.n_deep = &scal[1];
+  cp.out = o;
+  threadIdx.x = 0; blockDim.x = 1; gridDim.x = 1; blockIdx.x = 0;
+  classify_kernel(cp);
+  concat_queue_kernel(q_shallow.data(), q_deep.data(), &scal[0], &scal[1], queue.data(), &scal[2]);
+  blockDim.x = 32;
+  if (n_valid) *n_valid = scal[2];
+  if (n_shallow) *n_shallow = scal[0];
+  if (scal[2] == 0) return 0;
+  /* solve: as emu_invert, with the planes wired */
+  const int nsp = M.n_spatial == 0 ? 1 : M.n_spatial;
+  SolveParams sp;
+  memset(&sp, 0, sizeof(sp));
+  sp.L = make_layout(M.SB, M.n_scenes, M.n_bottoms, (2 * nsp - 1) * (2 * nsp - 1));
+  const long long simplex_doubles = (long long)(sp.L.nmax + 1) * sp.L.nmax;
+  const long long slab_doubles = simplex_doubles + sp.L.nmax + sp.L.Tmax + (long long)((sp.L.nmax + 8) / 8 + 1) * sp.L.nmax;
+  long long cache = simplex_smem_bytes;
+  if (cache > simplex_doubles * 8) cache = simplex_doubles * 8;
+  add_simplex_cache(sp.L, (int)cache);
+  sp.L.tmem_cols = 0;
+  if ((size_t)sp.L.cta_bytes + (size_t)sp.L.warp_bytes > sizeof(phb_smem)) return 2;
+  memset(phb_smem, 0xcd, sizeof(phb_smem));
+  std::vector<double> slab(slab_doubles, 0.0);
+  int head = 0;
+  unsigned long long cnt[4] = {0, 0, 0, 0};
+  double fl = 0.0;
+  sp.M = &M; sp.planes = planes; sp.prior = cp.prior;
+  sp.queue = queue.data(); sp.n_queue = &scal[2]; sp.head = &head;
+  sp.slabs = slab.data(); sp.slab_stride = slab_doubles;
+  sp.out = o;
+  sp.dbg_rec = rec; sp.dbg_pix = pix; sp.dbg_iters = iters; sp.reclen = emu_record_len(model); sp.dbg_capacity = (long long)win;
+  sp.counters = cnt; sp.flops = &fl;
+  sp.exp_tab = reinterpret_cast<const unsigned long long *>(kExpTab); sp.log_tab = kLogTab; sp.pow_tab = kPowTab;
+  if (sp.L.SBP == 32) g_kernel = M.n_bottoms == 3 ? solve_kernel<3, 32, false> : solve_kernel<0, 32, false>;
+  else g_kernel = M.n_bottoms == 3 ? solve_kernel<3, kMaxSB, false> : solve_kernel<0, kMaxSB, false>;
+  g_params = &sp;
+  g_body = body_solve;
+  run_warp();
   return 0;
 }
 

@@ -78,3 +78,40 @@ class Emulator:
                                         params.shape[0], vp(params), vp(out))
         assert rc == 0, rc
         return out
+
+    def invert_raster(self, desc, planes, prior, row_begin=0, row_end=None, simplex_smem_bytes=4096):
+        """The device side of phb_invert_device (classify, queue, solve) on a small raster. Returns the dict that
+        Inverter.invert_host(..., debug=True) returns: planes by name, K/P/G/X, converged, n_evals, rec / pix / ..."""
+        from photic_b200 import capi
+        L = capi.lib()
+        n = L.phb_debug_model_const(C.byref(desc), None, 0)
+        model = (C.c_ubyte * n)()
+        assert L.phb_debug_model_const(C.byref(desc), model, n) == n == self.lib.emu_model_const_size()
+        R, Cc, ns = desc.nrows, desc.ncols, desc.n_scenes
+        mb = max(desc.n_bands[s] for s in range(ns))
+        row_end = R if row_end is None else row_end
+        planes = np.ascontiguousarray(planes, dtype=np.float32)
+        pr = None if prior is None else np.ascontiguousarray(prior, dtype=np.float32)
+        out9 = np.full((9, R, Cc), 7.0, dtype=np.float32)
+        K = np.full((ns, mb, R, Cc), 7.0, dtype=np.float32)
+        P, G, X = (np.full((ns, R, Cc), 7.0, dtype=np.float32) for _ in range(3))
+        conv = np.full((R, Cc), 7, dtype=np.uint8)
+        nev = np.full((R, Cc), 7, dtype=np.int32)
+        cap = (row_end - row_begin) * Cc
+        reclen = self.lib.emu_record_len(model)
+        rec = np.zeros((cap, reclen))
+        pix = np.full(cap, -1, dtype=np.int32)
+        it = np.zeros((cap, 2), dtype=np.int32)
+        nv, nsh = C.c_int(0), C.c_int(0)
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+        rc = self.lib.emu_invert_raster(model, C.c_int64(n), vp(planes), C.c_void_p(None) if pr is None else vp(pr),
+                                        int(row_begin), int(row_end), int(simplex_smem_bytes), vp(out9), vp(K), vp(P), vp(G),
+                                        vp(X), vp(conv), vp(nev), vp(rec), vp(pix), vp(it), C.byref(nv), C.byref(nsh))
+        assert rc == 0, rc
+        nvalid = nv.value
+        order = np.argsort(pix[:nvalid], kind="stable")
+        out = dict(zip(capi.SCALAR_PLANES, out9))
+        out.update(K=K, P=P, G=G, X=X, converged=conv, n_evals=nev, rec=rec[:nvalid][order], pix=pix[:nvalid][order],
+                   rec_evals=it[:nvalid, 0][order], rec_converged=(it[:nvalid, 1] & 1)[order], n_valid=nvalid,
+                   n_shallow=nsh.value, queue_order=pix[:nvalid].copy())
+        return out

@@ -100,3 +100,41 @@ def test_emulated_variants_equal_oracle(product_lib, oracle_port, define):
     """The off-by-default experiment switches of the kernel are the same arithmetic in another order."""
     e = Emulator((define,), tag=define.split("=")[0].lower())
     _check(e, oracle_port, "exmouth", 12, 10, {}, 3, 6000)
+
+
+@pytest.mark.parametrize("name", ["scene_nspatial1", "scene_nsmooth2_nb2"])
+def test_emulated_device_pipeline_equals_reference_golden(emu, name):
+    """classify_kernel -> concat_queue_kernel -> solve_kernel on a whole (small) raster, against the committed outputs
+    of the UNMODIFIED reference: records, evaluation counts, convergence-flag map, the float planes samodel() leaves
+    (depth negated, K / P / G / X per scene) and the defaults where nothing is inverted (samodel.c:819-829)."""
+    from conftest import desc_from_golden, load_golden
+    g = load_golden(name)
+    desc = desc_from_golden(g)
+    _, R, C = g["planes"].shape
+    out = emu.invert_raster(desc, g["planes"], g["prior"] if bool(g["use_prior"]) else None, simplex_smem_bytes=3000)
+    ok = g["status"] == 1
+    pix = np.nonzero(ok)[0]
+    assert out["n_valid"] == ok.sum() and np.array_equal(out["pix"], pix)
+    assert np.array_equal(out["rec_evals"], g["n_evals"][ok]) and np.array_equal(out["rec_converged"], g["converged"][ok])
+    assert bits_equal(out["rec"], g["rec"][ok]).all()
+    rec, ns = out["rec"], len(g["theta_sun"])
+    i, j = pix // C, pix % C
+    assert np.array_equal(out["depth"][i, j], -(rec[:, 0].astype(np.float32)))
+    for col, plane in ((1, "model_error"), (2, "bottom_albedo"), (3, "bottom_sand"), (4, "bottom_seagrass"),
+                       (5, "bottom_coral"), (6, "K_min"), (7, "index_optical_depth"), (8, "bottom_type")):
+        assert np.array_equal(out[plane][i, j], rec[:, col].astype(np.float32)), plane
+    K = rec[:, 16:16 + ns * 4].reshape(-1, ns, 4).astype(np.float32)
+    assert np.array_equal(out["K"][:, :, i, j].transpose(2, 0, 1), K)
+    pgx = rec[:, 16 + ns * 4:16 + ns * 4 + 3 * ns].reshape(-1, ns, 3).astype(np.float32)
+    for k, plane in enumerate("PGX"):
+        assert np.array_equal(out[plane][:, i, j].T, pgx[:, :, k]), plane
+    assert np.array_equal(out["converged"].ravel(), g["converged"].astype(np.uint8))
+    assert np.array_equal(out["n_evals"].ravel(), g["n_evals"])
+    bad = ~ok.reshape(R, C)
+    assert (out["bottom_sand"][bad] == -9999.0).all() and (out["bottom_type"][bad] == -9999.0).all()
+    assert (out["depth"][bad] == 0.0).all() and np.signbit(out["depth"][bad]).all() and (out["K_min"][bad] == 0.0).all()
+    assert (out["K"][:, :, bad] == 0.0).all() and (out["P"][:, bad] == 0.0).all()
+    # the work queue: every shallow-water pixel (all substrates) before every sand-only one
+    q = out["queue_order"]
+    deep = np.abs(np.where(g["prior"].ravel()[q] > -1.0, -1.0, g["prior"].ravel()[q])) > 8.0 if bool(g["use_prior"]) else np.zeros(len(q), bool)
+    assert out["n_shallow"] == int((~deep).sum()) and not deep[:out["n_shallow"]].any() and deep[out["n_shallow"]:].all()
