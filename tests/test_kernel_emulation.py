@@ -138,3 +138,26 @@ def test_emulated_device_pipeline_equals_reference_golden(emu, name):
     q = out["queue_order"]
     deep = np.abs(np.where(g["prior"].ravel()[q] > -1.0, -1.0, g["prior"].ravel()[q])) > 8.0 if bool(g["use_prior"]) else np.zeros(len(q), bool)
     assert out["n_shallow"] == int((~deep).sum()) and not deep[:out["n_shallow"]].any() and deep[out["n_shallow"]:].all()
+
+
+def test_pixels_whose_objective_is_never_a_number(emu, oracle_port):
+    """An all-zero spectrum in the neighbourhood makes Rrs440/Rrs490 = 0/0 and with it every objective value NaN: no
+    start ever beats `lowest`, and the reference hands back uninitialised memory with n_iterations = 0
+    (samodel.c:2385-2413: `params` is only written when ynewlo < lowest). Here that case is defined: zero evaluations,
+    not converged, depth 0 -- and the oracle agrees on the counts. Huge and tiny reflectances stay ordinary pixels."""
+    from oracle.binding import SceneCfg
+    from photic_b200 import capi, scene
+    spec = scene.CONFIGS["murion"].scaled(9, 9)
+    planes, prior = scene.generate(spec)
+    pl, pr = planes.numpy().copy(), prior.numpy().copy()
+    pl[:] = np.where(pl < 0, np.float32(0.004), pl)  # no land
+    pl[:, 2, 2] = 0.0
+    pl[:, 6, 6] = 1e30
+    pl[:, 1, 5] = 1e-30
+    pi, pj = np.array([2, 3, 6, 1]), np.array([2, 3, 6, 5])
+    got = emu.invert_pixels(capi.desc_from_spec(spec), pl, pr, pi, pj)
+    ref = oracle_port.invert_pixels(SceneCfg.from_spec(spec), pl, scene.NODATA, pr, scene.NODATA, pi, pj)
+    assert np.array_equal(got["n_evals"], ref["n_evals"]) and np.array_equal(got["converged"], ref["converged"])
+    assert got["n_evals"][:2].tolist() == [0, 0] and got["converged"][:2].tolist() == [0, 0]
+    assert (got["planes"][0][pi[:2], pj[:2]] == 0.0).all() and (got["n_evals"][2:] > 100).all()
+    assert bits_equal(got["rec"][2:], ref["rec"][2:]).all()
