@@ -174,7 +174,9 @@ int phb_depth_sigma_host(phb_ctx *ctx, const phb_scene_desc *desc, const float *
 
 /* Parity-test hook: like phb_invert_host but also returns the full-precision per-pixel record
  * (layout of oracle/ref_harness.c: 16 + n_scenes*max_bands + 3*n_scenes doubles) for every
- * inverted pixel. rec: [capacity][reclen]; pix: [capacity] linear index i*ncols+j. */
+ * inverted pixel. rec: [capacity][reclen]; pix: [capacity] linear index i*ncols+j; n_iters (nullable): [capacity][3]
+ * = nelmin's icount of the best H start (md->n_iterations), converged | iterations << 1 of that start, and nelmin's
+ * restart count `numres` (asa047.c:493) summed over the H starts of the pixel. */
 int phb_debug_record_len(const phb_scene_desc *desc);
 int phb_invert_host_debug(phb_ctx *ctx, const phb_scene_desc *desc, const float *const *h_planes,
                           const float *h_prior, int row_begin, int row_end, const phb_outputs *h_out,

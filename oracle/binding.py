@@ -102,7 +102,8 @@ class Oracle:
         return out, out2
 
     def invert_pixels(self, cfg, planes, nodata, prior, prior_nodata, pix_i, pix_j, nthreads=0, variant=None):
-        """Per-pixel cold-start inversion. Returns dict(rec, status, converged, n_evals[, n_iters])."""
+        """Per-pixel cold-start inversion. Returns dict(rec, status, converged, n_evals, n_restarts[, n_iters]);
+        n_restarts = nelmin's numres (asa047.c:493) summed over the H starts of the pixel."""
         planes = _f(planes)
         _, nrows, ncols = planes.shape
         pix_i, pix_j = _i(pix_i), _i(pix_j)
@@ -115,13 +116,20 @@ class Oracle:
         tail = (C.c_int(cfg.n_smooth), C.c_int(cfg.n_spatial), C.c_int(cfg.n_bottoms), C.c_int(nrows), C.c_int(ncols),
                 _p(planes, _fp), C.c_float(nodata), prp, C.c_float(prior_nodata), C.c_int(npix), _p(pix_i, _ip),
                 _p(pix_j, _ip), _p(rec, _dp), _p(status, _ip), _p(conv, _ip), _p(nev, _ip))
+        nres = np.zeros(npix, dtype=np.int32)
+        has_numres = hasattr(self.lib, self.pre + "set_numres_out")  # a prebuilt oracle/_ref of round 1 has none
+        if has_numres:
+            self._fn("set_numres_out")(_p(nres, _ip))
         if variant is None:
             rc = self._fn("invert_pixels")(*cfg.head(), *tail, C.c_int(nthreads))
         else:
             assert self.kind == "port"
             rc = self.lib.pho_invert_pixels_variant(C.c_int(variant), *cfg.head(), *tail, _p(nit, _ip), C.c_int(nthreads))
+        if has_numres:
+            self._fn("set_numres_out")(C.cast(None, _ip))
         assert rc == 0, rc
-        return {"rec": rec, "status": status, "converged": conv, "n_evals": nev, "n_iters": nit}
+        return {"rec": rec, "status": status, "converged": conv, "n_evals": nev, "n_iters": nit,
+                "n_restarts": nres if has_numres else None}
 
     def error_kat(self, cfg, nb_active, n_regions, origin, meas, params):
         meas, params = _d(meas), _d(params)
@@ -192,13 +200,13 @@ class Oracle:
         return out
 
     def refine(self, grid, nodata, land, land_nodata, shallow, shallow_nodata, flags, args):
-        assert self.kind == "port"
+        """REFINE: pho_refine (restatement) or ref_refine (the reference's own run_refine(), refine.c:12-302)."""
         grid = _f(grid)
         out = np.zeros_like(grid)
         args = _f(args)
         ld = None if land is None else _f(land)
         sh = None if shallow is None else _f(shallow)
-        self.lib.pho_refine(C.c_int(grid.shape[0]), C.c_int(grid.shape[1]), _p(grid, _fp), C.c_float(nodata),
+        self._fn("refine")(C.c_int(grid.shape[0]), C.c_int(grid.shape[1]), _p(grid, _fp), C.c_float(nodata),
                             C.cast(None, _fp) if ld is None else _p(ld, _fp), C.c_float(land_nodata),
                             C.cast(None, _fp) if sh is None else _p(sh, _fp), C.c_float(shallow_nodata),
                             C.c_int(flags), _p(args, _fp), _p(out, _fp))

@@ -72,7 +72,7 @@ typedef struct {
   double e_rrs, e_depth, e_bottom, e_K, e_model;
   /* results */
   double depth, K_min, iod, pct[PHO_MAX_BOTTOMS], P[PHO_MAX_SCENES], G[PHO_MAX_SCENES], X[PHO_MAX_SCENES];
-  int bottom_type, converged, n_evals, n_iters;
+  int bottom_type, converged, n_evals, n_iters, n_restarts;
   int variant;
   int hot;                         /* md->start_at_previous */
   double prev[3 * PHO_MAX_SCENES]; /* md->prev: |P|,|G|,|X| (x100) of the previous optimum, samodel.c:2086-2097 */
@@ -560,6 +560,11 @@ static double objective_cb(const double *x, void *ctx) { return objective(x, (ph
  * per-pixel driver
  * ---------------------------------------------------------------------------------------- */
 
+/* where pho_invert_pixels reports nelmin's restart count (asa047.c:493) summed over the H starts of a pixel; same
+ * switch as ref_set_numres_out in oracle/ref_harness.c */
+static int *g_numres_out = NULL;
+void pho_set_numres_out(int *buf) { g_numres_out = buf; }
+
 /* samodel.c:2119-2427 */
 static void optimise_one_combination(pho_pixel *px, double *params) {
   const pho_model *m = px->m;
@@ -614,6 +619,7 @@ static void optimise_one_combination(pho_pixel *px, double *params) {
     icount = 0; numres = 0; ifault = 0;
     nelder_mead(objective_cb, px, n, start, xmin, &error, reqmin, step, konvge, kcount, &icount, &numres, &ifault,
                 &iters, px->variant);
+    px->n_restarts += numres;
     if (error < lowest) {
       lowest = error;
       for (i = 0; i < n; i++) best[i] = xmin[i];
@@ -762,7 +768,9 @@ int pho_invert_pixels_variant(int variant, int nscenes, int maxb, const int *n_b
           px->h_prior = (e > -1.0) ? 1.0 : fabs(e);
         }
       }
+      px->n_restarts = 0;
       optimise_pixel(px);
+      if (g_numres_out) g_numres_out[p] = px->n_restarts;
       status[p] = 1;
       converged[p] = px->converged;
       n_iterations[p] = px->n_evals;

@@ -150,6 +150,14 @@ static model_data *make_md(const ref_cfg *c) {
   return md;
 }
 
+/* restart counter of the wrapped nelmin (end of this file) and where ref_invert_pixels reports it */
+void ref_nelmin_counters_reset(void);
+int ref_nelmin_restarts(void);
+static int *g_numres_out = NULL;
+/* buf: [npix] ints filled by the next ref_invert_pixels calls with nelmin's restart count (asa047.c:493), summed
+ * over the H starts of the pixel; NULL switches it off */
+void ref_set_numres_out(int *buf) { g_numres_out = buf; }
+
 /* Number of doubles per pixel record written by ref_invert_pixels. */
 int ref_record_len(int nscenes, int maxb) { return 16 + nscenes * maxb + 3 * nscenes; }
 
@@ -260,7 +268,9 @@ int ref_invert_pixels(int nscenes, int maxb, const int *n_bands, const int *wave
       }
       md->start_at_previous = false;
       md->n_bottoms = n_bottoms;
+      ref_nelmin_counters_reset();
       samodel_optimise(md);
+      if (g_numres_out) g_numres_out[p] = ref_nelmin_restarts();
       status[p] = 1;
       converged[p] = md->converged ? 1 : 0;
       n_iterations[p] = md->n_iterations;
@@ -602,3 +612,80 @@ int ref_jerlov_k_from_ratio(float ratio, float wlen_i, float wlen_j, const float
   for (i = 0; i < n; i++) k[i] = 0.0f;
   return compute_k_from_ratio(ratio, wlen_i, wlen_j, water_type, k, (float *)wavelengths, (float)n) ? 1 : 0;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * REFINE: the reference's own run_refine() (refine.c:12-302, compiled where it lies). It is a REPL verb that reads
+ * its arguments from the tokenised command line `parsed[]` and its grids from the `gridded_data[]` / `grid_names[]`
+ * globals of common.h, so this driver writes the command the REPL would have tokenised
+ *   REFINE IN in OUT out [LAND land SHALLOW shallow] [SCRAP a b] [CLIP a b] [SCALE a b SHAPE s] [LINEAR m c] [POWER a b]
+ * (the order refine.c:118-213 parses them in) and registers the input grids in slots 0..2. Numbers are printed with
+ * %.9g, which atof() + the float assignment of refine.c turns back into exactly the float passed in.
+ * flags / args: layout of include/photic_b200.h (PHB_REFINE_*), the same as pho_refine in oracle/photic_oracle.c.
+ * ---------------------------------------------------------------------------------------- */
+void run_refine(void);
+
+static void ref_register_grid(int slot, const char *name, int nrows, int ncols, const float *data, float nodata) {
+  int r;
+  strcpy(grid_names[slot], name);
+  allocated_grids[slot] = true;
+  gridded_data[slot].nrows = nrows;
+  gridded_data[slot].ncols = ncols;
+  gridded_data[slot].nodata_value = nodata;
+  gridded_data[slot].array = (float **)malloc(nrows * sizeof(float *));
+  for (r = 0; r < nrows; r++) gridded_data[slot].array[r] = (float *)(data + (size_t)r * ncols);
+}
+
+int ref_refine(int nrows, int ncols, const float *in, float nodata, const float *land, float land_nodata,
+               const float *shallow, float shallow_nodata, int flags, const float *args, float *out) {
+  int k = 0, n, r, used = 1, ps_out = -1;
+  memset(parsed, 0, sizeof(parsed));
+  for (n = 0; n < MAX_GRIDS; n++) { allocated_grids[n] = false; grid_names[n][0] = '\0'; }
+  ref_register_grid(0, "in", nrows, ncols, in, nodata);
+  if (land) { ref_register_grid(used, "land", nrows, ncols, land, land_nodata); used++; }
+  if (shallow) { ref_register_grid(used, "shallow", nrows, ncols, shallow, shallow_nodata); used++; }
+  n_grids_in_use = used;
+#define TOK(s) strcpy(parsed[k++], s)
+#define NUM(v) snprintf(parsed[k++], MAX_ARG_SIZE, "%.9g", (double)(v))
+  TOK("REFINE"); TOK("IN"); TOK("in"); TOK("OUT"); TOK("out");
+  if (land) { TOK("LAND"); TOK("land"); }
+  if (shallow) { TOK("SHALLOW"); TOK("shallow"); }
+  if (flags & 8) { TOK("SCRAP"); NUM(args[7]); NUM(args[8]); }
+  if (flags & 1) { TOK("CLIP"); NUM(args[0]); NUM(args[1]); }
+  if (flags & 2) { TOK("SCALE"); NUM(args[2]); NUM(args[3]); TOK("SHAPE"); NUM(args[4]); }
+  if (flags & 4) { TOK("LINEAR"); NUM(args[5]); NUM(args[6]); }
+  if (flags & 16) { TOK("POWER"); NUM(args[9]); NUM(args[10]); }
+#undef TOK
+#undef NUM
+  run_refine();
+  for (n = 0; n < MAX_GRIDS; n++)
+    if (strcmp(grid_names[n], "out") == 0) ps_out = n;
+  if (ps_out < 0) return 1;
+  for (r = 0; r < nrows; r++) memcpy(out + (size_t)r * ncols, gridded_data[ps_out].array[r], ncols * sizeof(float));
+  free_float_array_2d(gridded_data[ps_out].array, nrows);
+  for (n = 0; n < used; n++) free(gridded_data[n].array);
+  for (n = 0; n < MAX_GRIDS; n++) { allocated_grids[n] = false; grid_names[n][0] = '\0'; gridded_data[n].array = NULL; }
+  n_grids_in_use = 0;
+  return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * nelmin's restart counter. samodel_optimise_one_bottom_combination keeps `numres` in a local
+ * (samodel.c:2146, 2373) and drops it; to see it without touching the reference sources the library is linked
+ * with -Wl,--wrap=nelmin: samodel.o's calls to nelmin arrive here, go on to the real nelmin (asa047.c:10), and
+ * the restart count of every call is added up per thread. ref_invert_pixels2 reports the total over the H starts
+ * of a pixel next to the usual record.
+ * ---------------------------------------------------------------------------------------- */
+void __real_nelmin(double fn(double x[], model_data *md), model_data *md, int n, double start[], double xmin[],
+                   double *ynewlo, double reqmin, double step[], int konvge, int kcount, int *icount, int *numres,
+                   int *ifault);
+static __thread int tl_numres_total = 0, tl_nelmin_calls = 0;
+void __wrap_nelmin(double fn(double x[], model_data *md), model_data *md, int n, double start[], double xmin[],
+                   double *ynewlo, double reqmin, double step[], int konvge, int kcount, int *icount, int *numres,
+                   int *ifault) {
+  __real_nelmin(fn, md, n, start, xmin, ynewlo, reqmin, step, konvge, kcount, icount, numres, ifault);
+  tl_numres_total += *numres;
+  tl_nelmin_calls += 1;
+}
+void ref_nelmin_counters_reset(void) { tl_numres_total = 0; tl_nelmin_calls = 0; }
+int ref_nelmin_restarts(void) { return tl_numres_total; }
+int ref_nelmin_calls(void) { return tl_nelmin_calls; }

@@ -464,7 +464,7 @@ static int invert_host_impl(phb_ctx *c, const phb_scene_desc *desc, const float 
   double *d_rec = nullptr; int *d_pix = nullptr, *d_it = nullptr;
   const int reclen = phb_debug_record_len(desc);
   if (rec && capacity > 0) {
-    CK(c->dbg_rec.ensure((size_t)capacity * reclen)); CK(c->dbg_pix.ensure(capacity)); CK(c->dbg_iters.ensure(2 * capacity));
+    CK(c->dbg_rec.ensure((size_t)capacity * reclen)); CK(c->dbg_pix.ensure(capacity)); CK(c->dbg_iters.ensure(3 * capacity));
     CK(cudaMemsetAsync(c->dbg_pix.p, 0xff, capacity * sizeof(int), st));
     d_rec = c->dbg_rec.p; d_pix = c->dbg_pix.p; d_it = c->dbg_iters.p;
   }
@@ -493,7 +493,7 @@ static int invert_host_impl(phb_ctx *c, const phb_scene_desc *desc, const float 
   if (d_rec) {
     CK(cudaMemcpyAsync(rec, d_rec, (size_t)capacity * reclen * sizeof(double), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(pix, d_pix, capacity * sizeof(int), cudaMemcpyDeviceToHost, st));
-    if (iters) CK(cudaMemcpyAsync(iters, d_it, 2 * capacity * sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (iters) CK(cudaMemcpyAsync(iters, d_it, 3 * capacity * sizeof(int), cudaMemcpyDeviceToHost, st));
   }
   CK(cudaEventRecord(e3, st));
   CK(cudaStreamSynchronize(st));

@@ -92,7 +92,7 @@ class Inverter:
             rl = self.lib.phb_debug_record_len(C.byref(desc))
             rec = np.zeros((cap, rl))
             pix = np.full(cap, -1, dtype=np.int32)
-            it = np.zeros((cap, 2), dtype=np.int32)
+            it = np.zeros((cap, 3), dtype=np.int32)
             check(self.lib.phb_invert_host_debug(self.ctx, C.byref(desc), ptrs, prp, row_begin, row_end, C.byref(o),
                                                  _np_ptr(rec, capi._dp), _np_ptr(pix, capi._ip), _np_ptr(it, capi._ip),
                                                  cap, C.byref(st)))
@@ -102,6 +102,7 @@ class Inverter:
             out["rec_evals"] = it[:n, 0][order]
             out["rec_converged"] = (it[:n, 1] & 1)[order]
             out["rec_iters"] = (it[:n, 1] >> 1)[order]
+            out["rec_restarts"] = it[:n, 2][order]  # nelmin's numres, summed over the H starts
         return out, st.as_dict()
 
     @staticmethod

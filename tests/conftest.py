@@ -82,3 +82,25 @@ def bits_equal(a, b):
 
 SCENE_FIXTURES = ["scene_murion", "scene_exmouth", "scene_qatar", "scene_noprior", "scene_nspatial1",
                   "scene_nsmooth2_nb2", "scene_nspatial3"]
+
+# Reference goldens for the rare pixels (tests/golden/make_golden.py: make_mined, make_restarts): nelmin's kcount
+# exhaustion (converged = 0), evaluation counts at the kcount edge, restarts after a failed factorial test. Patch k of
+# the raster = columns [3k, 3k+3); the reference inverted the patch centres (centre_i, centre_j).
+MINED_FIXTURES = ["mined_exmouth", "mined_qatar", "mined_abudhabi", "mined_pilbara", "mined_restart_exmouth",
+                  "mined_restart_qatar"]
+
+
+def refine_cases(g):
+    """(flags, land, land_nodata, shallow, shallow_nodata, args, expected) of tests/golden/refine.npz: the outputs of the
+    reference's own run_refine() (refine.c:12-302) for every flag set x {no mask, both, LAND only, SHALLOW only} x SHAPE."""
+    grid, land, shallow, args = g["grid"], g["land"], g["shallow"], g["args"]
+    for flags in (int(f) for f in g["flags"]):
+        for mk, (ld, sh) in enumerate(((None, None), (land, shallow), (land, None), (None, shallow))):
+            for shape1 in (0, 1):
+                key = f"out_{flags}_{mk}_{shape1}"
+                if key not in g.files:
+                    continue
+                a2 = args.copy()
+                if shape1:
+                    a2[4] = 1.0
+                yield flags, ld, -9999.0, sh, -7777.0, a2, g[key]

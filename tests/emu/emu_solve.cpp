@@ -177,7 +177,7 @@ int emu_record_len(const void *model) {
  * One warp inverts the queued pixels with the product kernel. model: ModelConst bytes (phb_debug_model_const);
  * planes [SB][nrows][ncols], prior [nrows][ncols] or null; queue: linear pixel indices; simplex_smem_bytes: shared
  * memory given to the warp for simplex rows (the rest of the simplex lives in the "global" slab, checkpoints and all);
- * outputs: full-precision records [n_queue][reclen] + pixel index + (evals, converged | iters << 1), the nine result
+ * outputs: full-precision records [n_queue][reclen] + pixel index + (evals, converged | iters << 1, nelmin restarts), the nine result
  * planes (out9, [9][nrows][ncols], nullable), converged / n_evals planes (nullable), counters[4], flops.
  */
 int emu_invert(const void *model, int64_t model_size, const float *planes, const float *prior, const int *queue,

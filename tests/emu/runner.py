@@ -48,7 +48,7 @@ class Emulator:
         nq, reclen = len(q), self.lib.emu_record_len(model)
         rec = np.zeros((nq, reclen))
         pix = np.full(nq, -1, dtype=np.int32)
-        it = np.zeros((nq, 2), dtype=np.int32)
+        it = np.zeros((nq, 3), dtype=np.int32)
         out9 = np.full((9, desc.nrows, desc.ncols), 7.0, dtype=np.float32)
         conv = np.zeros((desc.nrows, desc.ncols), dtype=np.uint8)
         nev = np.zeros((desc.nrows, desc.ncols), dtype=np.int32)
@@ -60,7 +60,8 @@ class Emulator:
                                  C.byref(fl))
         assert rc == 0, rc
         assert np.array_equal(pix, q)
-        return {"rec": rec, "n_evals": it[:, 0], "converged": it[:, 1] & 1, "n_iters": it[:, 1] >> 1, "planes": out9,
+        return {"rec": rec, "n_evals": it[:, 0], "converged": it[:, 1] & 1, "n_iters": it[:, 1] >> 1, "n_restarts": it[:, 2],
+                "planes": out9,
                 "converged_plane": conv, "n_evals_plane": nev, "counters": cnt, "alg_flops": fl.value}
 
     def kat_objective(self, desc, nb_active, n_regions, origin, meas, params):
@@ -101,7 +102,7 @@ class Emulator:
         reclen = self.lib.emu_record_len(model)
         rec = np.zeros((cap, reclen))
         pix = np.full(cap, -1, dtype=np.int32)
-        it = np.zeros((cap, 2), dtype=np.int32)
+        it = np.zeros((cap, 3), dtype=np.int32)
         nv, nsh = C.c_int(0), C.c_int(0)
         vp = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
         rc = self.lib.emu_invert_raster(model, C.c_int64(n), vp(planes), C.c_void_p(None) if pr is None else vp(pr),
@@ -112,6 +113,7 @@ class Emulator:
         order = np.argsort(pix[:nvalid], kind="stable")
         out = dict(zip(capi.SCALAR_PLANES, out9))
         out.update(K=K, P=P, G=G, X=X, converged=conv, n_evals=nev, rec=rec[:nvalid][order], pix=pix[:nvalid][order],
-                   rec_evals=it[:nvalid, 0][order], rec_converged=(it[:nvalid, 1] & 1)[order], n_valid=nvalid,
+                   rec_evals=it[:nvalid, 0][order], rec_converged=(it[:nvalid, 1] & 1)[order], rec_restarts=it[:nvalid, 2][order],
+                   n_valid=nvalid,
                    n_shallow=nsh.value, queue_order=pix[:nvalid].copy())
         return out

@@ -290,8 +290,145 @@ def make_jerlov():
         ratio_wt=np.array([r[4] for r in ratios], dtype=np.float32), ratio_k=np.stack([r[5] for r in ratios]))
 
 
+# (config, non-converged pixels kept, high-evaluation-count converged pixels kept)
+MINED = (("exmouth", 40, 10), ("qatar", 40, 10), ("abudhabi", 10, 6), ("pilbara", 17, 6))
+
+
+def make_mined():
+    """Reference goldens for the pixels the small scenes never contain: nelmin's `ifault = 2` (kcount exhausted,
+    asa047.c:217, 411-453, 481-493 -> md->converged = false, samodel.c:2396-2402), restarts after a failed factorial
+    test (numres >= 1) and evaluation counts at the kcount edge. The pixels were found on the GPU in full-size scenes
+    (tests/manual/mine_nonconverged.py -> gpurun_out/mined_<config>.npz: 3x3 input neighbourhoods side by side, patch
+    k = columns [3k, 3k+3), centre (1, 3k+1), global coordinates kept). Here the UNMODIFIED reference inverts the
+    centres of a subset; the device's own evaluation counts / flags from the mining run are kept beside them only as
+    a record (the tests compare fresh device results with the reference's)."""
+    build()
+    ref = Oracle("reference")
+    for name, n_nonconv, n_high in MINED:
+        src = os.path.join(ROOT, "gpurun_out", f"mined_{name}.npz")
+        if not os.path.exists(src):
+            print("skip", name, "(no mining output)")
+            continue
+        m = np.load(src)
+        spec = scene.CONFIGS[name]
+        conv, ev = m["dev_converged"], m["dev_evals"]
+        bad = np.nonzero(conv == 0)[0]
+        bad = bad[np.linspace(0, len(bad) - 1, min(n_nonconv, len(bad))).round().astype(int)]
+        good = np.nonzero(conv == 1)[0]
+        _, first = np.unique(ev[good], return_index=True)      # one pixel per distinct evaluation count, highest first
+        good = good[np.sort(first)][:n_high]
+        keep = np.concatenate([bad, good])
+        K = len(keep)
+        planes = np.concatenate([m["planes"][:, :, 3 * k:3 * k + 3] for k in keep], axis=2)
+        prior = np.concatenate([m["prior"][:, 3 * k:3 * k + 3] for k in keep], axis=1)
+        ci, cj = np.ones(K, dtype=np.int32), (3 * np.arange(K) + 1).astype(np.int32)
+        cfg = SceneCfg.from_spec(spec)
+        out = ref.invert_pixels(cfg, planes, scene.NODATA, prior, scene.NODATA, ci, cj, nthreads=8)
+        assert (out["status"] == 1).all()
+        agree = int((out["n_evals"] == ev[keep]).sum())
+        np.savez_compressed(
+            os.path.join(HERE, f"mined_{name}.npz"), planes=planes, prior=prior, use_prior=True,
+            wavelengths=np.array(spec.wavelengths), theta_view=spec.theta_view,
+            theta_sun=np.array([spec.theta_sun(s) for s in range(spec.n_dates)]),
+            h_tide=np.array([spec.h_tide(s) for s in range(spec.n_dates)]), n_smooth=spec.n_smoothing_radius,
+            n_spatial=spec.n_spatial, n_bottoms=spec.n_bottoms, nodata=scene.NODATA, centre_i=ci, centre_j=cj,
+            global_i=m["gi"][keep], global_j=m["gj"][keep], rec=out["rec"], status=out["status"],
+            converged=out["converged"], n_evals=out["n_evals"], n_restarts=out["n_restarts"],
+            mining_run_evals=ev[keep], mining_run_converged=conv[keep])
+        print(f"mined_{name}: {K} centres, reference says non-converged {int((out['converged'] == 0).sum())}, "
+              f"restarts>=1 {int((out['n_restarts'] >= 1).sum())}, max evals {int(out['n_evals'].max())}, "
+              f"mining-run evaluation counts equal to the reference's: {agree}/{K}")
+
+
+# pixels of seeded small scenes whose factorial test fails once and restarts nelmin (numres = 1, asa047.c:445-493),
+# found with the CPU restatement (n_restarts of oracle.binding.Oracle.invert_pixels): (config, rows, cols, pixels)
+RESTARTS = (("exmouth", 160, 140, ((55, 39), (60, 135))), ("qatar", 120, 120, ((90, 86),)))
+
+
+def make_restarts():
+    """Same patch layout as make_mined() for pixels on which nelmin restarts (numres >= 1), each with its right-hand
+    neighbour as an ordinary pixel beside it; the reference's restart count comes from the wrapped nelmin of
+    oracle/ref_harness.c (the reference keeps numres in a local and drops it, samodel.c:2146, 2373)."""
+    build()
+    ref = Oracle("reference")
+    for name, R, Cc, pixels in RESTARTS:
+        spec = scene.CONFIGS[name].scaled(R, Cc)
+        planes, prior = scene.generate(spec)
+        planes, prior = planes.numpy(), prior.numpy()
+        pts = [q for (i, j) in pixels for q in ((i, j), (i, j + 1))]
+        pp = np.concatenate([planes[:, i - 1:i + 2, j - 1:j + 2] for i, j in pts], axis=2)
+        pr = np.concatenate([prior[i - 1:i + 2, j - 1:j + 2] for i, j in pts], axis=1)
+        K = len(pts)
+        ci, cj = np.ones(K, dtype=np.int32), (3 * np.arange(K) + 1).astype(np.int32)
+        out = ref.invert_pixels(SceneCfg.from_spec(spec), pp, scene.NODATA, pr, scene.NODATA, ci, cj, nthreads=4)
+        assert (out["n_restarts"][::2] >= 1).all(), out["n_restarts"]
+        np.savez_compressed(
+            os.path.join(HERE, f"mined_restart_{name}.npz"), planes=pp, prior=pr, use_prior=True,
+            wavelengths=np.array(spec.wavelengths), theta_view=spec.theta_view,
+            theta_sun=np.array([spec.theta_sun(s) for s in range(spec.n_dates)]),
+            h_tide=np.array([spec.h_tide(s) for s in range(spec.n_dates)]), n_smooth=spec.n_smoothing_radius,
+            n_spatial=spec.n_spatial, n_bottoms=spec.n_bottoms, nodata=scene.NODATA, centre_i=ci, centre_j=cj,
+            global_i=np.array([p[0] for p in pts], dtype=np.int32), global_j=np.array([p[1] for p in pts], dtype=np.int32),
+            rec=out["rec"], status=out["status"], converged=out["converged"], n_evals=out["n_evals"],
+            n_restarts=out["n_restarts"])
+        print(f"mined_restart_{name}: restarts", out["n_restarts"].tolist(), "evals", out["n_evals"].tolist(), "status",
+              out["status"].tolist())
+
+
+REFINE_FLAGS = (0, 1, 2, 3, 4, 8, 16, 1 | 2 | 4 | 8 | 16, 2 | 16, 1 | 8, 2 | 4, 1 | 2 | 16)  # include/photic_b200.h PHB_REFINE_*
+
+
+def refine_inputs():
+    """Inputs of the REFINE goldens (also regenerated by the tests: only the outputs need storing)."""
+    rng = np.random.default_rng(11)
+    grid = (-rng.uniform(0.2, 35.0, (57, 43))).astype(np.float32)
+    grid[rng.uniform(size=grid.shape) < 0.2] = -9999.0
+    grid[3, 4], grid[5, 6], grid[7, 8] = 2.5, 0.0, -9998.5   # positive depth, zero, a value approx_equal() to nodata at 1e-4
+    land = np.where(rng.uniform(size=grid.shape) < 0.3, -9999.0, 1.0).astype(np.float32)
+    shallow = np.where(rng.uniform(size=grid.shape) < 0.2, -7777.0, 1.0).astype(np.float32)
+    args = np.array([-30.0, -0.5, -40.0, 0.0, 1.3, 0.9, -0.25, -32.0, -1.0, 1.1, 0.95], dtype=np.float32)
+    return grid, land, shallow, args
+
+
+def make_refine():
+    """REFINE through the reference's own run_refine() (refine.c:12-302, driven by ref_refine in oracle/ref_harness.c):
+    every flag set of the GPU test, with both masks, one mask only (the reference then blanks the whole grid,
+    refine.c:242-244) and none; SHAPE 1.0 (linear rescale branch); min/max taken from the grid when CLIP is absent."""
+    build()
+    ref = Oracle("reference")
+    grid, land, shallow, args = refine_inputs()
+    res = {"grid": grid, "land": land, "shallow": shallow, "args": args, "flags": np.array(REFINE_FLAGS, dtype=np.int32)}
+    sys.stdout.flush()
+    saved = os.dup(1)
+    devnull = os.open(os.devnull, os.O_WRONLY)
+    os.dup2(devnull, 1)  # run_refine printf()s its POWER arguments
+    try:
+        for flags in REFINE_FLAGS:
+            for mk, (ld, sh) in enumerate(((None, None), (land, shallow), (land, None), (None, shallow))):
+                for shape1 in (0, 1):
+                    if shape1 and not (flags & 2):
+                        continue
+                    a2 = args.copy()
+                    if shape1:
+                        a2[4] = 1.0
+                    res[f"out_{flags}_{mk}_{shape1}"] = ref.refine(grid, -9999.0, ld, -9999.0, sh, -7777.0, flags, a2)
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(devnull)
+    np.savez_compressed(os.path.join(HERE, "refine.npz"), **res)
+    print("refine:", sum(k.startswith("out_") for k in res), "cases;", "open cells in the full-flag case",
+          int((res["out_31_1_0"] != -9999.0).sum()))
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "depth_sigma":
+    if len(sys.argv) > 1 and sys.argv[1] == "refine":
+        make_refine()
+    elif len(sys.argv) > 1 and sys.argv[1] == "mined":
+        make_mined()
+    elif len(sys.argv) > 1 and sys.argv[1] == "restarts":
+        make_restarts()
+    elif len(sys.argv) > 1 and sys.argv[1] == "depth_sigma":
         make_depth_sigma()
     elif len(sys.argv) > 1 and sys.argv[1] == "lee_ls8":
         make_lee_ls8()
@@ -305,3 +442,6 @@ if __name__ == "__main__":
         make_lee_ls8()
         make_jerlov()
         make_kat_extreme()
+        make_refine()
+        make_mined()
+        make_restarts()

@@ -7,7 +7,7 @@ from dataclasses import replace
 import numpy as np
 import pytest
 
-from conftest import SCENE_FIXTURES, bits_equal, cfg_from_golden, desc_from_golden, load_golden
+from conftest import MINED_FIXTURES, SCENE_FIXTURES, bits_equal, cfg_from_golden, desc_from_golden, load_golden
 
 pytestmark = pytest.mark.gpu
 
@@ -55,6 +55,33 @@ def test_golden_scenes_bit_exact(inverter, name):
     bad = ~ok.reshape(R, C)
     assert (out["bottom_sand"][bad] == -9999.0).all() and (out["bottom_type"][bad] == -9999.0).all()
     assert (out["depth"][bad] == 0.0).all() and (out["K_min"][bad] == 0.0).all()
+
+
+@pytest.mark.parametrize("name", MINED_FIXTURES)
+def test_mined_non_converged_and_restart_pixels_bit_exact(inverter, name):
+    """Reference goldens of the rare pixels (tests/golden/make_golden.py make_mined / make_restarts): the device's
+    `ifault = 2` exit (kcount exhausted -> converged 0 with more than 5000 evaluations, asa047.c:217, 411-453 ->
+    samodel.c:2396-2402), the budget hit exactly with a passing factorial test, and nelmin restarts (numres >= 1,
+    asa047.c:481-493) must equal the UNMODIFIED reference: full record, evaluation count, flag, restart count."""
+    g = load_golden(name)
+    desc = desc_from_golden(g)
+    _, R, C = g["planes"].shape
+    out, st = inverter.invert_host(desc, g["planes"], g["prior"], debug=True)
+    centres = g["centre_i"].astype(np.int64) * C + g["centre_j"]
+    sel = np.searchsorted(out["pix"], centres)
+    assert np.array_equal(out["pix"][sel], centres)
+    assert np.array_equal(out["rec_converged"][sel], g["converged"])
+    assert np.array_equal(out["rec_evals"][sel], g["n_evals"])
+    assert np.array_equal(out["rec_restarts"][sel], g["n_restarts"])
+    assert bits_equal(out["rec"][sel], g["rec"]).all()
+    # the flag / count planes the shim hands back carry the same values
+    assert np.array_equal(out["converged"][g["centre_i"], g["centre_j"]], g["converged"].astype(np.uint8))
+    assert np.array_equal(out["n_evals"][g["centre_i"], g["centre_j"]], g["n_evals"])
+    if "restart" in name:
+        assert (out["rec_restarts"][sel] >= 1).any()
+    else:
+        assert (out["rec_converged"][sel] == 0).sum() >= 10
+    assert st["n_converged"] == int(out["rec_converged"].sum())
 
 
 @pytest.mark.parametrize("cfg_name,R,C,over", [
@@ -335,6 +362,19 @@ def test_refine_matches_oracle(inverter, oracle_port):
             got = inverter.refine_host(grid, -9999.0, flags, a2, land=masks[0], shallow=masks[1])
             exp = oracle_port.refine(grid, -9999.0, masks[0], -9999.0, masks[1], -9999.0, flags, a2)
             assert np.array_equal(got.view(np.int32), exp.view(np.int32)), (flags, masks[0] is not None)
+
+
+def test_refine_matches_reference_golden(inverter):
+    """REFINE kernels against the outputs of the reference's own run_refine() (tests/golden/refine.npz, made by
+    oracle/_ref with refine.c compiled in): 72 cases incl. one-mask-only (whole grid blanked), no-CLIP min/max, SHAPE 1."""
+    from conftest import refine_cases
+    g = load_golden("refine")
+    n = 0
+    for flags, ld, ldn, sh, shn, args, exp in refine_cases(g):
+        got = inverter.refine_host(g["grid"], -9999.0, flags, args, land=ld, land_nodata=ldn, shallow=sh, shallow_nodata=shn)
+        assert np.array_equal(got.view(np.int32), exp.view(np.int32)), (flags, ld is not None, sh is not None)
+        n += 1
+    assert n == 72
 
 
 def test_python_samodel_surface(inverter):

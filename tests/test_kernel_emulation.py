@@ -161,3 +161,23 @@ def test_pixels_whose_objective_is_never_a_number(emu, oracle_port):
     assert got["n_evals"][:2].tolist() == [0, 0] and got["converged"][:2].tolist() == [0, 0]
     assert (got["planes"][0][pi[:2], pj[:2]] == 0.0).all() and (got["n_evals"][2:] > 100).all()
     assert bits_equal(got["rec"][2:], ref["rec"][2:]).all()
+
+
+@pytest.mark.parametrize("name,take", [("mined_exmouth", (0, 20, 45)), ("mined_restart_exmouth", (0, 2)),
+                                       ("mined_restart_qatar", (0,))])
+def test_emulated_kernel_on_mined_reference_pixels(emu, name, take):
+    """The kernel source on the reference's goldens of the rare exits (tests/golden/make_golden.py make_mined /
+    make_restarts): kcount exhausted (`ifault = 2`, converged 0, asa047.c:217, 411-453), the budget hit exactly with a
+    passing factorial test, and a restart after a failed one (numres = 1, asa047.c:481-493)."""
+    from conftest import desc_from_golden, load_golden
+    g = load_golden(name)
+    desc = desc_from_golden(g)
+    k = np.array(take)
+    got = emu.invert_pixels(desc, g["planes"], g["prior"], g["centre_i"][k], g["centre_j"][k], simplex_smem_bytes=8192)
+    assert np.array_equal(got["n_evals"], g["n_evals"][k]) and np.array_equal(got["converged"], g["converged"][k])
+    assert np.array_equal(got["n_restarts"], g["n_restarts"][k])
+    assert bits_equal(got["rec"], g["rec"][k]).all()
+    if name == "mined_exmouth":
+        assert got["converged"].tolist() == [0, 0, 1] and (got["n_evals"] > 5000).all()
+    else:
+        assert (got["n_restarts"] == 1).all()
