@@ -6,11 +6,13 @@
     python bench.py --impl reference ...                               (the reference's CPU code)
 
 Workload (config.workload): BASELINE.json configs[1], the Exmouth-Gulf-shaped 3930x2858, 6-date
-synthetic Landsat-8 scene, cut into `--batches` row batches. One STEP inverts one batch per GPU
-(weak scaling: N GPUs take N batches per step, stacked into one raster that is sharded by row bands
-with a real NCCL halo exchange and a final gather of the output planes to rank 0). Every step sees
-a different batch (134 MB of reflectance planes per batch > the 126 MB L2), so nothing is cached
-between timed iterations.
+synthetic Landsat-8 scene, cut into `--batches` row batches (default 2: 1965 rows, ~0.77 M valid pixels).
+One STEP inverts one batch -- the SAME raster at every N (strong scaling): at N GPUs the batch is held
+as N equal row bands, one per rank, halo rows are exchanged point to point (NCCL), the solve kernels
+share the work at run time over NVLink (a device that runs out of pixels takes them from its
+neighbours' queues: photic_b200.sharded.BandGroup), and the nine result planes are gathered on rank 0.
+Consecutive steps see different batches (>= 335 MB of reflectance planes each > the 126 MB L2), so
+nothing is cached between timed iterations.
 
 Printed JSON line (rank 0): `value` = valid pixels inverted / device time with inputs resident in
 HBM; `e2e` = the same through the host-buffer C-ABI call (pinned host memory in, host planes out,
@@ -45,9 +47,9 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="exmouth")
-    ap.add_argument("--batches", type=int, default=0,
-                    help="row batches the scene is cut into (one per GPU per step); default = --steps, so that the "
-                         "timed steps cover every batch of the scene exactly N times at N GPUs")
+    ap.add_argument("--batches", type=int, default=2,
+                    help="row batches the scene is cut into; one batch = the raster of one step, at every N")
+    ap.add_argument("--no-share", action="store_true", help="N > 1: every rank works on its own band only")
     ap.add_argument("--rows", type=int, default=0, help="debug: shrink the scene")
     ap.add_argument("--cols", type=int, default=0)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU work of the cpu_baseline sample")
@@ -103,52 +105,72 @@ def batch_rows(spec, args, b):
     return r0, min(spec.nrows, r0 + rb)
 
 
-def cpu_baseline(spec, args, planes_np, prior_np, target_s, steps=1):
+def cpu_sample(planes_np, n, offset=0):
+    """every k-th valid pixel, starting at `offset`: distinct pixels for distinct offsets < k"""
+    from photic_b200 import scene
+    import torch
+    vm = scene.valid_mask(torch.from_numpy(planes_np)).numpy()
+    ii, jj = np.nonzero(vm)
+    n = int(max(64, min(len(ii), n)))
+    k = max(1, len(ii) // n)
+    sel = np.arange(offset % k, len(ii), k)[:n]
+    return ii[sel], jj[sel], k
+
+
+def cpu_baseline(spec, args, planes_np, prior_np, target_s):
     """The reference's CPU inversion on a bounded, deterministic pixel sample (every k-th valid pixel)."""
     from oracle.binding import REF_SO, Oracle, SceneCfg
     from photic_b200 import scene
-    import torch
     kind = "reference" if os.path.exists(REF_SO) else "port"
     orc = Oracle(kind)
     cores = len(os.sched_getaffinity(0))
-    vm = scene.valid_mask(torch.from_numpy(planes_np)).numpy()
-    ii, jj = np.nonzero(vm)
-    n = int(max(64, min(len(ii), cores * 25 * target_s)))  # ~25 px/s/core at 6 dates (BASELINE.md)
-    k = max(1, len(ii) // n)
-    sel = np.arange(0, len(ii), k)[:n]
-    cfg = SceneCfg.from_spec(spec)
-    times = []
-    for _ in range(steps):
-        t = time.time()
-        out = orc.invert_pixels(cfg, planes_np, scene.NODATA, prior_np, scene.NODATA, ii[sel], jj[sel], nthreads=cores)
-        times.append(time.time() - t)
-    pxs = len(sel) / float(np.mean(times))
-    return {"value": pxs, "unit": UNIT, "cores": cores, "kind": kind,
-            "sample": f"every {k}th valid pixel of batch 0 ({len(sel)} px, {np.mean(times):.1f} s/step, "
-                      f"omp schedule(dynamic), gcc -O3, mean {out['n_evals'].mean():.0f} evals/px)"}, times, len(sel)
+    ii, jj, k = cpu_sample(planes_np, cores * 25 * target_s)  # ~25 px/s/core at 6 dates (BASELINE.md)
+    t = time.time()
+    out = orc.invert_pixels(SceneCfg.from_spec(spec), planes_np, scene.NODATA, prior_np, scene.NODATA, ii, jj, nthreads=cores)
+    dt = time.time() - t
+    return {"value": len(ii) / dt, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": f"every {k}th valid pixel of batch 0 ({len(ii)} px, {dt:.1f} s, omp schedule(dynamic), gcc -O3, "
+                      f"mean {out['n_evals'].mean():.0f} evals/px)"}
 
 
 def run_reference(args, emit=print):
-    """--impl reference: the reference's own CPU implementation, all host threads, same workload."""
+    """--impl reference: the reference's own CPU implementation (oracle/_ref: the unmodified samodel.c / asa047.c /
+    common.c per-pixel cold start under omp schedule(dynamic)), all host threads, same workload. Every step times a
+    different sample of a different batch; the timed steps together cover >= 50 000 distinct pixels."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    from oracle.binding import REF_SO, Oracle, SceneCfg
     from photic_b200 import scene
     spec = scene_spec(args)
-    r0, r1 = batch_rows(spec, args, 0)
-    planes, prior = scene.generate(spec, r0, r1)
-    planes_np, prior_np = planes.numpy(), prior.numpy()
-    sub = spec.scaled(r1 - r0, spec.ncols)
-    per_step = max(4.0, min(20.0, 150.0 / max(1, args.steps + args.warmup)))
-    base, times, npx = cpu_baseline(sub, args, planes_np, prior_np, per_step, steps=args.warmup + args.steps)
-    t = times[args.warmup:]
-    val = npx * len(t) / float(np.sum(t))
-    base["value"] = val
+    kind = "reference" if os.path.exists(REF_SO) else "port"
+    orc = Oracle(kind)
+    cores = len(os.sched_getaffinity(0))
+    K, W = args.steps, args.warmup
+    per_step = int(min(20000, max(2000, -(-50000 // max(1, K)))))
+    data = {}
+    for b in sorted({s % args.batches for s in range(W + K)}):
+        r0, r1 = batch_rows(spec, args, b)
+        planes, prior = scene.generate(spec, r0, r1)
+        data[b] = (planes.numpy(), prior.numpy(), spec.scaled(r1 - r0, spec.ncols))
+    times, npx, evals = [], [], []
+    for s in range(W + K):
+        pl, pr, sub = data[s % args.batches]
+        ii, jj, k = cpu_sample(pl, per_step if s >= W else min(per_step, 2000), offset=s // args.batches)
+        t = time.time()
+        out = orc.invert_pixels(SceneCfg.from_spec(sub), pl, scene.NODATA, pr, scene.NODATA, ii, jj, nthreads=cores)
+        times.append(time.time() - t); npx.append(len(ii)); evals.append(float(out["n_evals"].mean()))
+    t, n = times[W:], npx[W:]
+    val = float(np.sum(n)) / float(np.sum(t))
+    base = {"value": val, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": f"{int(np.sum(n))} distinct valid pixels in {K} timed steps ({n[0]} per step, every k-th valid pixel of "
+                      f"batch s mod {args.batches}, start offset s div {args.batches}), {np.mean(t):.1f} s/step, "
+                      f"omp schedule(dynamic) on {cores} threads, gcc -O3, mean {np.mean(evals[W:]):.0f} evals/px"}
     emit(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(t)), "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": K,
+        "warmup": W, "ms_per_step": 1e3 * float(np.mean(t)), "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(spec, args, 1, extra={"sample_px_per_step": npx}),
+        "config": workload_config(spec, args, args.gpus),
         "cpu_baseline": base, "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
 
@@ -158,9 +180,10 @@ def workload_config(spec, args, world, extra=None):
     c = {"workload": f"{spec.name} {spec.nrows}x{spec.ncols}, {spec.n_dates} dates x {spec.n_bands} bands "
                      f"(BASELINE.json configs[1]), NSPATIAL={spec.n_spatial} NSMOOTH={spec.n_smoothing_radius} "
                      f"NBOTTOMS={spec.n_bottoms}, DEPTHS prior",
-         "step": f"one batch of {rb} rows x {spec.ncols} cols per GPU ({args.batches} batches per scene), a new batch every step",
-         "l2": "inputs larger than L2: every step reads a different batch (>=134 MB of planes)",
-         "parallelism": f"row bands x{world}" + (", cost-balanced re-deal + halo exchange (NCCL p2p) + gather" if world > 1 else "")}
+         "step": f"one batch of {rb} rows x {spec.ncols} cols ({args.batches} batches per scene), the same raster at every "
+                 f"GPU count, another batch every step",
+         "l2": "inputs larger than L2: consecutive steps read different batches (>= 335 MB of planes each)",
+         "parallelism": f"row bands x{world}"}
     if extra:
         c.update(extra)
     return c
@@ -168,8 +191,7 @@ def workload_config(spec, args, world, extra=None):
 
 def main():
     args = parse()
-    if args.batches <= 0:
-        args.batches = max(1, args.steps)
+    args.batches = max(1, args.batches)
     # stdout carries exactly ONE line, the JSON result: everything else that libraries print there (NCCL's
     # "NCCL version ..." banner, OpenMP notices) is sent to stderr for the duration of the run.
     sys.stdout.flush()
@@ -201,52 +223,46 @@ def main():
     spec = scene_spec(args)
     K, W = args.steps, args.warmup
     halo = sharded.halo_rows(spec.n_spatial, spec.n_smoothing_radius)
-    rb = -(-spec.nrows // args.batches)
-    plan_eq = [(r * rb, (r + 1) * rb) for r in range(world)]  # how the stacked per-step raster arrives
+    rb = -(-spec.nrows // args.batches)          # rows of one batch = the raster of one step
+    plan = sharded.equal_row_bands(rb, world)    # equal row bands: the kernels share the work at run time
+    r0b, r1b = plan[rank]
+    w0, w1, lb, le = sharded.window(r0b, r1b, halo, rb)
 
-    # ---- resident inputs: the batches this rank will see, generated on the device ----------------
-    def batch_of(step, r=None):
-        return (step * world + (rank if r is None else r)) % args.batches
+    # ---- resident inputs: this rank's rows of every batch it will see, generated on the device --------
+    def batch_of(step):
+        return step % args.batches
 
     need = sorted({batch_of(s) for s in range(W + K)})
-    data, cost = {}, {}
+    data = {}
     for b in need:
-        r0, r1 = batch_rows(spec, args, b)
-        p, pr = scene.generate(spec, r0, r1, device=dev)
-        if r1 - r0 < rb:  # last batch of the scene may be short: pad with nodata rows (land)
-            padp = torch.full((p.shape[0], rb - (r1 - r0), spec.ncols), scene.NODATA, device=dev)
-            p = torch.cat([p, padp], dim=1).contiguous()
-            pr = torch.cat([pr, torch.full((rb - (r1 - r0), spec.ncols), scene.NODATA, device=dev)], dim=0).contiguous()
+        g0, g1 = batch_rows(spec, args, b)
+        a0, a1 = min(g1, g0 + r0b), min(g1, g0 + r1b)
+        if a1 > a0:
+            p, pr = scene.generate(spec, a0, a1, device=dev)
+        else:
+            p = torch.empty((spec.n_planes, 0, spec.ncols), device=dev)
+            pr = torch.empty((0, spec.ncols), device=dev)
+        if a1 - a0 < r1b - r0b:  # the last batch of the scene may be short: pad with nodata rows (land)
+            padn = (r1b - r0b) - (a1 - a0)
+            p = torch.cat([p, torch.full((p.shape[0], padn, spec.ncols), scene.NODATA, device=dev)], dim=1).contiguous()
+            pr = torch.cat([pr, torch.full((padn, spec.ncols), scene.NODATA, device=dev)], dim=0).contiguous()
         data[b] = (p, pr)
-        # estimated work per row: a shallow-water pixel (all substrates) costs ~3x a sand-only one
-        cost[b] = sharded.row_cost_from_prior(scene.valid_mask(p), pr)
     torch.cuda.synchronize()
     peak_tflops, _ = inv.fp64_peak()
     gather_names = capi.SCALAR_PLANES
-    out_cache = {}
+    group = sharded.BandGroup(inv, capi.desc_from_spec(spec, nrows=w1 - w0), lb, le, rank, world,
+                              share=not args.no_share)
+    band = group.band
 
     def step(s):
-        """One step: N batches stacked into one raster; rows are re-dealt to cost-balanced bands (NCCL p2p),
-        halo rows exchanged, every rank inverts its band, the 9 result planes are gathered on rank 0."""
+        """One step: the batch is held as N equal row bands; halo rows are exchanged (NCCL p2p), every rank inverts its
+        band and then takes pixels from its neighbours' queues, the 9 result planes are gathered on rank 0."""
         p, pr = data[batch_of(s)]
-        plan = plan_eq
+        band.planes.copy_(sharded.exchange_halo(p, plan, halo, rank, world))
+        band.prior.copy_(sharded.exchange_halo(pr[None], plan, halo, rank, world)[0])
+        st = group.step()
         if world > 1:
-            c = torch.zeros(rb * world, device=dev)
-            c[rank * rb:(rank + 1) * rb] = cost[batch_of(s)]
-            dist.all_reduce(c)
-            plan = sharded.plan_row_bands(c.cpu().numpy(), world)
-            p = sharded.repartition_rows(p, plan_eq, plan, rank, world)
-            pr = sharded.repartition_rows(pr[None], plan_eq, plan, rank, world)[0]
-        win = sharded.exchange_halo(p, plan, halo, rank, world)
-        prw = sharded.exchange_halo(pr[None], plan, halo, rank, world)[0]
-        w0, w1, lb, le = sharded.window(plan[rank][0], plan[rank][1], halo, rb * world)
-        if w1 - w0 not in out_cache:
-            d = capi.desc_from_spec(spec, nrows=w1 - w0)
-            out_cache[w1 - w0] = (d, Inverter.alloc_device_outputs(d, dev, scene_planes=False))
-        desc, outs = out_cache[w1 - w0]
-        st = inv.invert_device(desc, win.contiguous(), prw.contiguous(), outs, row_begin=lb, row_end=le)
-        if world > 1:
-            stack = torch.stack([outs[n][lb:le] for n in gather_names])
+            stack = torch.stack([band.outputs[n][lb:le] for n in gather_names])
             sharded.gather_bands(stack, plan, rank, world)
         return st
 
@@ -281,46 +297,58 @@ def main():
     value = total_px / (total_ms * 1e-3)
 
     # ---- end to end through the host-buffer C-ABI call ------------------------------------------------
+    # N = 1: phb_invert_host. N > 1: phb_invert_host_multi from ONE process (rank 0) over the N devices of the box --
+    # the plugin's own multi-GPU entry point, what the samodel() shim calls -- while the other ranks wait.
     e2e = None
     if not args.no_e2e:
-        hp, hpr = {}, {}
-        for b in need:
-            p, pr = data[b]
-            hp[b] = torch.empty(p.shape, dtype=torch.float32, pin_memory=True).copy_(p).numpy()
-            hpr[b] = torch.empty(pr.shape, dtype=torch.float32, pin_memory=True).copy_(pr).numpy()
-        hdesc = capi.desc_from_spec(spec, nrows=rb)
-        hbuf = {n: torch.empty((rb, spec.ncols), dtype=torch.float32, pin_memory=True).numpy() for n in capi.SCALAR_PLANES}
-        hbuf["converged"] = torch.empty((rb, spec.ncols), dtype=torch.uint8, pin_memory=True).numpy()
-        hbuf["n_evals"] = torch.empty((rb, spec.ncols), dtype=torch.int32, pin_memory=True).numpy()
-
-        def host_step(s):
-            b = batch_of(s)
-            _, st = inv.invert_host(hdesc, hp[b], hpr[b], scene_planes=False, buffers=hbuf)
-            return st
-
-        host_step(0)
         if world > 1:
             dist.barrier()
-        t0 = time.perf_counter()
-        hst = [host_step(W + s) for s in range(K)]
-        t1 = time.perf_counter()
-        tt = torch.tensor([t1 - t0], dtype=torch.float64, device=dev)
-        hpx = torch.tensor([float(sum(s["n_valid"] for s in hst))], dtype=torch.float64, device=dev)
+        if rank == 0:
+            hp, hpr = {}, {}
+            for b in need:
+                g0, g1 = batch_rows(spec, args, b)
+                p, pr = scene.generate(spec, g0, g1)
+                hp[b] = torch.full((spec.n_planes, rb, spec.ncols), scene.NODATA, dtype=torch.float32).pin_memory()
+                hpr[b] = torch.full((rb, spec.ncols), scene.NODATA, dtype=torch.float32).pin_memory()
+                hp[b][:, : g1 - g0].copy_(p)
+                hpr[b][: g1 - g0].copy_(pr)
+                hp[b], hpr[b] = hp[b].numpy(), hpr[b].numpy()
+            hdesc = capi.desc_from_spec(spec, nrows=rb)
+            hbuf = {n: torch.empty((rb, spec.ncols), dtype=torch.float32, pin_memory=True).numpy() for n in capi.SCALAR_PLANES}
+            hbuf["converged"] = torch.empty((rb, spec.ncols), dtype=torch.uint8, pin_memory=True).numpy()
+            hbuf["n_evals"] = torch.empty((rb, spec.ncols), dtype=torch.int32, pin_memory=True).numpy()
+            ivs = [inv] + [Inverter(k) for k in range(1, world)]
+
+            def host_step(s):
+                b = batch_of(s)
+                if world == 1:
+                    _, st = inv.invert_host(hdesc, hp[b], hpr[b], scene_planes=False, buffers=hbuf)
+                else:
+                    _, st = Inverter.invert_host_multi(ivs, hdesc, hp[b], hpr[b], scene_planes=False, buffers=hbuf)
+                return st
+
+            host_step(0)
+            t0 = time.perf_counter()
+            hst = [host_step(W + s) for s in range(K)]
+            t1 = time.perf_counter()
+            for iv in ivs[1:]:
+                iv.close()
+            plane_bytes = rb * spec.ncols * 4
+            e2e = {"value": float(sum(s["n_valid"] for s in hst)) / (t1 - t0), "unit": UNIT,
+                   "h2d_bytes_per_step": plane_bytes * (spec.n_planes + 1),
+                   "d2h_bytes_per_step": plane_bytes * len(capi.SCALAR_PLANES) + rb * spec.ncols * 5,
+                   "ms_per_step": 1e3 * (t1 - t0) / K,
+                   "api": "phb_invert_host (pinned host planes in, host planes out)" if world == 1 else
+                          f"phb_invert_host_multi from one process over {world} devices (pinned host planes in, host planes out)"}
         if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            dist.all_reduce(hpx)
-        plane_bytes = rb * spec.ncols * 4
-        e2e = {"value": float(hpx[0]) / float(tt[0]), "unit": UNIT,
-               "h2d_bytes_per_step": world * plane_bytes * (spec.n_planes + 1),
-               "d2h_bytes_per_step": world * (plane_bytes * len(capi.SCALAR_PLANES) + rb * spec.ncols * 5),
-               "ms_per_step": 1e3 * float(tt[0]) / K}
+            dist.barrier()
 
     if rank == 0:
         alg_flops, ms_solve = float(agg[0]), float(agg[1]) / world
         achieved = alg_flops / (ms_solve * 1e-3) / 1e12 / world  # per-GPU TFLOP/s of the solve kernel
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": workload_config(spec, args, world),
             "pixels_per_step": total_px / K,
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
@@ -333,7 +361,8 @@ def main():
             "stats": {"shallow_fraction": float(agg[4]) / total_px, "converged_fraction": float(agg[5]) / total_px,
                       "warps_per_cta": stats[0]["warps_per_cta"], "ctas": stats[0]["ctas"],
                       "smem_bytes": stats[0]["smem_bytes"], "regs": stats[0]["regs"]},
-            "e2e": e2e, "gpu_launches": 3 * K * world, "clocks": clocks,
+            "work_sharing": bool(stats[0].get("shared", False)),
+            "e2e": e2e, "gpu_launches": 2 * K * world, "clocks": clocks,
         }
         # measured DRAM traffic of the kernel: bytes per pixel from the committed `ncu --set full` capture x pixels per launch
         tpath = os.path.join(ROOT, "profiles", "r01_solve_kernel_traffic.json")
@@ -343,11 +372,10 @@ def main():
             line["roofline"]["traffic_source"] = "profiles/r01_solve_kernel_traffic.json (ncu dram__bytes_read+write per pixel) x pixels per launch"
         # algorithmic HBM traffic (reported, not binding): planes + prior in, 9 planes + flags out
         bytes_px = spec.n_planes * 4 + 4 + 9 * 4 + 5
-        line["roofline"]["hbm_gbs_algorithmic"] = bytes_px * rb * spec.ncols * K * world / (total_ms * 1e-3) / 1e9
+        line["roofline"]["hbm_gbs_algorithmic"] = bytes_px * rb * spec.ncols * K / (total_ms * 1e-3) / 1e9
         if not args.no_cpu_baseline and world == 1:
             p, pr = data[need[0]]
-            base, _, _ = cpu_baseline(spec.scaled(rb, spec.ncols), args, p.cpu().numpy(), pr.cpu().numpy(), args.cpu_seconds)
-            line["cpu_baseline"] = base
+            line["cpu_baseline"] = cpu_baseline(spec.scaled(rb, spec.ncols), args, p.cpu().numpy(), pr.cpu().numpy(), args.cpu_seconds)
         emit(json.dumps(line))
     if world > 1:
         dist.barrier()

@@ -40,7 +40,8 @@ enum {
   PHB_ENODEVICE = 2, /* no usable CUDA device (there is no CPU fallback)   */
   PHB_ECUDA = 3,     /* a CUDA call failed; see phb_error_string           */
   PHB_ENOMEM = 4,    /* host or device allocation failed                   */
-  PHB_ENOFIT = 5     /* phb_jerlov_*: the reference's `return false` paths  */
+  PHB_ENOFIT = 5,    /* phb_jerlov_*: the reference's `return false` paths  */
+  PHB_ENOPEER = 6    /* a peer band cannot be mapped (no peer access between the devices / IPC refused) */
 };
 
 /*
@@ -64,6 +65,10 @@ typedef struct phb_scene_desc {
   float prior_nodata;
   double r_sigma[PHB_MAX_SCENES][PHB_MAX_BANDS];      /* scene.R_sigma (SCENE ... RSIGMA, bam.c:1474): only the
                                                          depth-error trials read it (samodel.c:3004-3006)  */
+  int32_t nodata_per_band;                            /* != 0: nodata_band[][] holds every grid's own nodata_value --
+                                                         the reference tests band k against gridded_data[k].nodata_value
+                                                         (samodel.c:683, 941, 2999-3003); 0: all grids share `nodata` */
+  float nodata_band[PHB_MAX_SCENES][PHB_MAX_BANDS];
 } phb_scene_desc;
 
 /*
@@ -123,21 +128,25 @@ int phb_band_tables(const phb_scene_desc *desc, double *out_tables, double *out_
 int phb_invert_device(phb_ctx *ctx, const phb_scene_desc *desc, const float *d_planes, const float *d_prior,
                       int row_begin, int row_end, const phb_outputs *d_out, void *stream, phb_stats *stats);
 
-/* Same with HOST buffers: copies in, inverts, copies out (what the samodel() shim calls). */
+/* Same with HOST buffers: copies in (through a pinned staging ring, so pageable caller memory streams at PCIe speed),
+ * inverts, copies out. */
 int phb_invert_host(phb_ctx *ctx, const phb_scene_desc *desc, const float *const *h_planes, const float *h_prior,
                     int row_begin, int row_end, const phb_outputs *h_out, phb_stats *stats);
 
 /*
  * One process, several GPUs: what the reference's OpenMP team is to its cores. The scene is cut into
- * contiguous row bands of near-equal estimated cost (valid pixels weighted by the depth bin of their DEPTHS prior:
- * shallow-water pixels carry all NBOTTOMS substrates and cost ~2.5x a sand-only one), each band is inverted by one
- * context -- one per device -- on its own host thread, reading its rows plus (n_spatial-1)+(n_smoothing_radius-1)
- * halo rows straight from the caller's host planes and writing its rows of the caller's output planes. Pixels are
- * independent given the read-only halo, so there is no exchange between devices and the result equals
- * phb_invert_host() on one device bit for bit.
- *   ctxs      n_ctx contexts from phb_ctx_create (normally one per device; two on one device also work)
- *   stats     sums over the bands, times = the slowest band; per_ctx (nullable) [n_ctx]; edges_out (nullable)
- *             [n_ctx + 1]: band k = rows [edges[k], edges[k+1])
+ * contiguous row bands, one per context -- one context per device -- each on its own host thread, which copies its
+ * rows plus (n_spatial-1)+(n_smoothing_radius-1) halo rows straight from the caller's host rasters to its device and
+ * its rows of the results back. Pixels are independent given the read-only halo, so the result equals phb_invert_host()
+ * on one device bit for bit. Load balance: where the devices can map each other's memory (NVLink / NVSwitch peer
+ * access) the bands are EQUAL row counts and the solve kernels share the work at run time -- a device whose own queue is
+ * empty takes pixels from its neighbours' queues, reads their neighbourhoods from the owner's planes and stores the
+ * results into the owner's planes over NVLink (phb_shard_* below) -- as the reference's `omp schedule(dynamic)` does
+ * for cores (samodel.c:902). Without peer access the bands are planned by estimated cost instead (valid pixels weighted
+ * by the depth bin of their DEPTHS prior; phb_plan_row_bands) and every device works on its own band only.
+ *   ctxs      n_ctx contexts from phb_ctx_create (normally one per device; several on one device also work)
+ *   stats     sums over the devices, times = the slowest device; per_ctx (nullable) [n_ctx]: what each DEVICE did
+ *             (incl. pixels taken from neighbours); edges_out (nullable) [n_ctx + 1]: band k = rows [edges[k], edges[k+1])
  * phb_plan_row_bands is the planner on its own (host only, no device): edges [n_parts + 1], row_cost (nullable) [nrows].
  */
 int phb_plan_row_bands(const phb_scene_desc *desc, const float *const *h_planes, const float *h_prior, int n_parts,
@@ -145,6 +154,52 @@ int phb_plan_row_bands(const phb_scene_desc *desc, const float *const *h_planes,
 int phb_invert_host_multi(phb_ctx *const *ctxs, int n_ctx, const phb_scene_desc *desc, const float *const *h_planes,
                           const float *h_prior, const phb_outputs *h_out, phb_stats *stats, phb_stats *per_ctx,
                           int32_t *edges_out);
+
+/*
+ * The same two entry points for rasters held the way the reference holds them: `float **array`, one malloc per row
+ * (geogrid.array, common.c:562-572). Rows are copied straight from / to the caller's row pointers through the pinned
+ * staging ring -- no packed intermediate copy of the scene on the host (Pilbara: 26 GB of reflectance planes).
+ *   plane_rows [sum_s n_bands[s]][nrows] row pointers, scene-major then band; prior_rows [nrows] or NULL
+ *   out        row pointers per result grid; any member may be NULL
+ */
+typedef struct phb_row_outputs {
+  float *const *depth, *const *model_error, *const *bottom_albedo, *const *bottom_sand, *const *bottom_seagrass,
+      *const *bottom_coral, *const *K_min, *const *bottom_type, *const *index_optical_depth; /* [nrows] */
+  float *const *const *K;                           /* [n_scenes * max_bands][nrows] */
+  float *const *const *P, *const *const *G, *const *const *X; /* [n_scenes][nrows] */
+} phb_row_outputs;
+int phb_invert_rows(phb_ctx *const *ctxs, int n_ctx, const phb_scene_desc *desc, const float *const *const *plane_rows,
+                    const float *const *prior_rows, const phb_row_outputs *out, phb_stats *stats, phb_stats *per_ctx,
+                    int32_t *edges_out);
+
+/*
+ * A row band of a scene resident on one device, shareable with the other devices of the box. This is
+ * the device-resident form of the multi-GPU path: one band per device -- one process per device (torch.distributed) or
+ * all in one process -- each exported as a POD handle (CUDA IPC across processes, peer access inside one) that the
+ * other devices open. phb_shard_solve() then runs the persistent solve kernel over the device's OWN queue first and
+ * its peers' queues after: work moves between devices pixel by pixel over NVLink, with no collective on the data path
+ * and no cost model.
+ *   create    desc->nrows = rows of the band's raster INCLUDING its halo rows; [row_begin,row_end) = the rows of that
+ *             raster this band owns (are inverted / carry results). scene_planes != 0: K/P/G/X planes too.
+ *   buffers   device pointers of the band's own rasters: the caller fills d_planes [SB][nrows][ncols] and d_prior
+ *             (NULL when desc->prior_present == 0) before prepare, and reads d_out after solve.
+ *   prepare   validity scan, output defaults, work queues (asynchronous on `stream`).
+ *   solve     peers [n_peers]: handles of the other bands in the order this device should take work from them
+ *             (exclude its own). EVERY band must have finished prepare before ANY solve starts, and results are complete
+ *             only after EVERY device's solve has finished: the caller synchronises (barrier / events) at both points.
+ *             stats: what THIS device computed (n_valid counts the pixels it inverted, its own or its neighbours').
+ * PHB_ENOPEER when a peer cannot be mapped; the caller then runs the bands independently (n_peers = 0).
+ */
+typedef struct phb_shard phb_shard;
+typedef struct phb_shard_handle { unsigned char bytes[512]; } phb_shard_handle;
+int phb_shard_create(phb_ctx *ctx, const phb_scene_desc *desc, int row_begin, int row_end, int scene_planes,
+                     phb_shard **out);
+int phb_shard_buffers(phb_shard *s, float **d_planes, float **d_prior, phb_outputs *d_out);
+int phb_shard_export(phb_shard *s, phb_shard_handle *h);
+int phb_shard_prepare(phb_shard *s, void *stream);
+int phb_shard_solve(phb_shard *s, const phb_shard_handle *peers, int n_peers, void *stream, phb_stats *stats);
+int64_t phb_shard_valid(phb_shard *s); /* valid pixels of the band's own rows (after prepare; synchronises) */
+void phb_shard_destroy(phb_shard *s);
 
 /*
  * Depth-error estimate, the last phase of samodel() (samodel.c:1376-1477): for every 0.25 m depth interval

@@ -38,6 +38,8 @@ class SceneDesc(C.Structure):
         ("prior_present", C.c_int32),
         ("prior_nodata", C.c_float),
         ("r_sigma", (C.c_double * MAX_BANDS) * MAX_SCENES),
+        ("nodata_per_band", C.c_int32),
+        ("nodata_band", (C.c_float * MAX_BANDS) * MAX_SCENES),
     ]
 
 
@@ -57,6 +59,22 @@ class Stats(C.Structure):
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+class ShardHandle(C.Structure):
+    """phb_shard_handle: where a row band lives (CUDA IPC handle / owner pointer) and its view as offsets. POD: ranks
+    exchange it as bytes (torch.distributed all_gather of a uint8 tensor)."""
+    _fields_ = [("bytes", C.c_ubyte * 512)]
+
+
+_fpp = C.POINTER(_fp)
+
+
+class RowOutputs(C.Structure):
+    """phb_row_outputs: result grids as row pointers (the reference's float **)."""
+    _fields_ = [(n, _fpp) for n in ("depth", "model_error", "bottom_albedo", "bottom_sand", "bottom_seagrass",
+                                    "bottom_coral", "K_min", "bottom_type", "index_optical_depth")]
+    _fields_ += [(n, C.POINTER(_fpp)) for n in ("K", "P", "G", "X")]
 
 
 SCALAR_PLANES = ("depth", "model_error", "bottom_albedo", "bottom_sand", "bottom_seagrass", "bottom_coral", "K_min",
@@ -111,6 +129,17 @@ def lib() -> C.CDLL:
         L.phb_invert_host_multi.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.POINTER(SceneDesc), C.POINTER(C.c_void_p),
                                             C.c_void_p, C.POINTER(Outputs), C.POINTER(Stats), C.POINTER(Stats),
                                             C.POINTER(C.c_int32)]
+        L.phb_invert_rows.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.POINTER(SceneDesc), C.c_void_p, C.c_void_p,
+                                      C.POINTER(RowOutputs), C.POINTER(Stats), C.POINTER(Stats), C.POINTER(C.c_int32)]
+        L.phb_shard_create.argtypes = [C.c_void_p, C.POINTER(SceneDesc), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        L.phb_shard_buffers.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(Outputs)]
+        L.phb_shard_export.argtypes = [C.c_void_p, C.POINTER(ShardHandle)]
+        L.phb_shard_prepare.argtypes = [C.c_void_p, C.c_void_p]
+        L.phb_shard_solve.argtypes = [C.c_void_p, C.POINTER(ShardHandle), C.c_int, C.c_void_p, C.POINTER(Stats)]
+        L.phb_shard_valid.argtypes = [C.c_void_p]
+        L.phb_shard_valid.restype = C.c_int64
+        L.phb_shard_destroy.argtypes = [C.c_void_p]
+        L.phb_shard_destroy.restype = None
         L.phb_debug_model_const.argtypes = [C.POINTER(SceneDesc), C.c_void_p, C.c_int64]
         L.phb_debug_model_const.restype = C.c_int64
         L.phb_jerlov_fit.argtypes = [C.c_float, C.c_float, C.c_float, C.c_float, _fp, _fp, C.c_int, C.c_float, _fp,
@@ -121,41 +150,55 @@ def lib() -> C.CDLL:
     return _lib
 
 
-PHB_OK, PHB_EINVAL, PHB_ENODEVICE, PHB_ECUDA, PHB_ENOMEM, PHB_ENOFIT = range(6)  # include/photic_b200.h
+PHB_OK, PHB_EINVAL, PHB_ENODEVICE, PHB_ECUDA, PHB_ENOMEM, PHB_ENOFIT, PHB_ENOPEER = range(7)  # include/photic_b200.h
 
 EXPORTS = ["phb_version", "phb_error_string", "phb_device_count", "phb_ctx_create", "phb_ctx_destroy",
            "phb_band_tables", "phb_invert_device", "phb_invert_host", "phb_debug_record_len", "phb_invert_host_debug",
            "phb_kat_objective", "phb_kat_math", "phb_refine_minmax_device", "phb_refine_device", "phb_refine_host",
            "phb_fp64_peak", "phb_depth_sigma_host", "phb_lee_ls8_device", "phb_lee_ls8_host",
            "phb_jerlov_fit", "phb_jerlov_k", "phb_jerlov_k_from_ratio",
-           "phb_plan_row_bands", "phb_invert_host_multi", "phb_debug_model_const"]
+           "phb_plan_row_bands", "phb_invert_host_multi", "phb_debug_model_const", "phb_invert_rows",
+           "phb_shard_create", "phb_shard_buffers", "phb_shard_export", "phb_shard_prepare", "phb_shard_solve",
+           "phb_shard_valid", "phb_shard_destroy"]
 
 
 def check(rc: int) -> None:
     if rc != 0:
-        raise PhoticError(f"photic_b200 error {rc}: {lib().phb_error_string(rc).decode()}")
+        e = PhoticError(f"photic_b200 error {rc}: {lib().phb_error_string(rc).decode()}")
+        e.code = rc
+        raise e
 
 
 def make_desc(wavelengths, theta_view, theta_sun, h_tide, nrows, ncols, nodata=-9999.0, prior_present=True,
-              prior_nodata=-9999.0, n_smooth=1, n_spatial=2, n_bottoms=3, r_sigma=1.0e-4) -> SceneDesc:
-    wl = np.asarray(wavelengths, dtype=np.int32)
+              prior_nodata=-9999.0, n_smooth=1, n_spatial=2, n_bottoms=3, r_sigma=1.0e-4, nodata_band=None) -> SceneDesc:
+    """wavelengths: one band list for every scene, or one list PER scene -- the lists may differ in length (mixed
+    sensors: the reference and the C ABI allow a different n_bands per scene, samodel.c:403-409). r_sigma: scalar or
+    per scene per band (ragged allowed). nodata_band: per scene per band nodata values (every grid is tested against
+    its own, samodel.c:683) or None when all grids share `nodata`."""
     ns = len(theta_sun)
-    if wl.ndim == 1:
-        wl = np.tile(wl, (ns, 1))
+    per_scene = len(wavelengths) > 0 and not np.isscalar(wavelengths[0])
+    wls = [list(wavelengths[s]) for s in range(ns)] if per_scene else [list(wavelengths)] * ns
     d = SceneDesc()
     d.n_scenes = ns
     tv = np.broadcast_to(np.asarray(theta_view, dtype=np.float64), (ns,))
     for s in range(ns):
-        d.n_bands[s] = wl.shape[1]
-        for b in range(wl.shape[1]):
-            d.wavelengths[s][b] = int(wl[s, b])
-            d.r_sigma[s][b] = float(np.broadcast_to(np.asarray(r_sigma, dtype=np.float64), wl.shape)[s, b])
+        d.n_bands[s] = len(wls[s])
+        for b in range(len(wls[s])):
+            d.wavelengths[s][b] = int(wls[s][b])
+            if np.isscalar(r_sigma):
+                d.r_sigma[s][b] = float(r_sigma)
+            else:
+                row = r_sigma[s]
+                d.r_sigma[s][b] = float(row[b]) if b < len(row) else 0.0
+            if nodata_band is not None:
+                d.nodata_band[s][b] = float(nodata_band[s][b])
         d.theta_view[s] = float(tv[s])
         d.theta_sun[s] = float(theta_sun[s])
         d.h_tide[s] = float(h_tide[s])
     d.n_smoothing_radius, d.n_spatial, d.n_bottoms = n_smooth, n_spatial, n_bottoms
     d.nrows, d.ncols = nrows, ncols
     d.nodata = nodata
+    d.nodata_per_band = 0 if nodata_band is None else 1
     d.prior_present = 1 if prior_present else 0
     d.prior_nodata = prior_nodata
     return d

@@ -17,7 +17,7 @@ __global__ void kat_objective_kernel(const SolveParams p, int nb_active, int n_r
   __syncthreads();
   Warp w;
   const int lane = threadIdx.x & 31, SB = p.L.SB, Ns = p.L.Ns;
-  bind_warp(w, p, phb_smem, 0, 0);
+  bind_warp(w, p, p.L, phb_smem, 0, 0);
   Pixel px;
   px.Nr = n_regions; px.Nb = nb_active; px.origin = origin;
   size_pixel(px, lane, SB, Ns, p.L.simplex_doubles, 0);

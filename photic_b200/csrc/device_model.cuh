@@ -27,6 +27,8 @@ struct ModelConst {
   int n_scenes, SB, n_bottoms, n_spatial, n_smooth, max_bands;
   int nrows, ncols, prior_present;
   float nodata, prior_nodata;
+  float nodata_sb[kMaxSB]; /* geogrid.nodata_value of each (scene,band) grid: every band is tested against its OWN grid's
+                              value (samodel.c:683, 941, 2999-3003); all equal to `nodata` unless the caller says otherwise */
   int n_bands[kMaxS];
   int sb_begin[kMaxS + 1]; /* first flattened (scene,band) index of scene s */
   int s_of[kMaxSB];        /* scene of a flattened index */

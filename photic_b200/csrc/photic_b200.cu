@@ -13,6 +13,11 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <unistd.h>
+
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -120,6 +125,7 @@ void build_model(const phb_scene_desc *d, ModelConst *M) {
       M->agexp[sb] = exp(arg);
       M->ratio440[sb] = 440.0 / w;
       M->r_sigma[sb] = d->r_sigma[s][b];
+      M->nodata_sb[sb] = d->nodata_per_band ? d->nodata_band[s][b] : d->nodata;
     }
     for (int g = 0; g < 4; g++) {
       Bracket B = resolve_bracket(lam, d->n_bands[s], targets[g]);
@@ -146,6 +152,10 @@ struct DevBuf {
   void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
+constexpr int kMaxViews = 64;          /* bands a solve kernel can take work from (its own + peers) */
+constexpr size_t kRingBytes = 16u << 20; /* one slot of the pinned staging ring */
+constexpr int kScalars = 8;            /* [0] n class 0 (all substrates) [1] n class 1 (sand only) [2] n both [3] head 0 [4] head 1 */
+
 }  // namespace
 
 struct phb_ctx {
@@ -156,23 +166,82 @@ struct phb_ctx {
   ModelConst *d_model = nullptr;
   unsigned long long *d_exp_tab = nullptr;
   double *d_log_tab = nullptr, *d_pow_tab = nullptr;
-  DevBuf<int> q_shallow, q_deep, queue;
-  int *d_scalars = nullptr;              /* [0] n_shallow [1] n_deep [2] n_queue [3] head */
+  DevBuf<int> q_shallow, q_deep, queue;  /* queues of phb_invert_device (caller-owned rasters) and the trial arrays */
+  int *d_scalars = nullptr;              /* kScalars ints */
   unsigned long long *d_counters = nullptr; /* 4 counters */
   double *d_flops = nullptr;
+  BandView *d_views = nullptr;           /* kMaxViews */
   DevBuf<double> slabs;
-  /* host entry staging */
-  DevBuf<float> planes, prior, outs;
-  DevBuf<unsigned char> conv;
+  DevBuf<float> planes, prior, outs;     /* staging of the depth-error / REFINE / Lee host entries */
   DevBuf<int> nev;
   DevBuf<double> dbg_rec;
   DevBuf<int> dbg_pix, dbg_iters;
+  phb_shard *host_shard = nullptr;       /* the band of the host entry points, kept between calls */
+  float *ring[2] = {nullptr, nullptr};   /* pinned staging ring (host entry points) */
+  cudaEvent_t ring_ev[2] = {nullptr, nullptr};
   cudaEvent_t ev[4];
 };
 
+/* A row band resident on one device: one allocation (so one IPC handle) holding the rasters, the work queues and the
+ * result planes, and the BandView that describes it in the owner's address space. */
+struct phb_shard {
+  phb_ctx *ctx = nullptr;
+  phb_scene_desc desc;
+  ModelConst M;
+  int row_begin = 0, row_end = 0, SB = 0, mb = 0, Ns = 0, scene_planes = 0, two_classes = 0;
+  unsigned char *base = nullptr;
+  size_t bytes = 0;
+  BandView view;
+  int *scalars = nullptr, *q_shallow = nullptr, *q_deep = nullptr, *q_all = nullptr;
+  struct Mapped { long long pid; unsigned long long base; unsigned char *ptr; bool ipc; };
+  std::vector<Mapped> mapped;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  /* debug records of the next solve (parity tests; own band only) */
+  double *dbg_rec = nullptr; int *dbg_pix = nullptr, *dbg_iters = nullptr; long long dbg_cap = 0;
+};
+
+namespace {
+
+/* what a handle carries: where the band lives and its view as OFFSETS into the allocation */
+struct HandleData {
+  uint32_t magic;
+  int32_t device;
+  int64_t pid;
+  uint64_t base, bytes;
+  int32_t ipc_ok, nrows, ncols, two_classes;
+  cudaIpcMemHandle_t ipc;
+  uint64_t off[8 + 15]; /* planes, prior, queue[2], n_queue[2], head[2], then the 15 members of phb_outputs */
+};
+static_assert(sizeof(HandleData) <= sizeof(phb_shard_handle), "handle too small");
+constexpr uint32_t kHandleMagic = 0x50484253u; /* "PHBS" */
+constexpr uint64_t kNullOff = ~0ull;
+
+/* the pointer members of a BandView in a fixed order (out: the 15 members of phb_outputs in declaration order) */
+void view_pointers(BandView &v, const void **slots[23]) {
+  int k = 0;
+  slots[k++] = (const void **)&v.planes; slots[k++] = (const void **)&v.prior;
+  slots[k++] = (const void **)&v.queue[0]; slots[k++] = (const void **)&v.queue[1];
+  slots[k++] = (const void **)&v.n_queue[0]; slots[k++] = (const void **)&v.n_queue[1];
+  slots[k++] = (const void **)&v.head[0]; slots[k++] = (const void **)&v.head[1];
+  phb_outputs &o = v.out;
+  slots[k++] = (const void **)&o.depth; slots[k++] = (const void **)&o.model_error; slots[k++] = (const void **)&o.bottom_albedo;
+  slots[k++] = (const void **)&o.bottom_sand; slots[k++] = (const void **)&o.bottom_seagrass; slots[k++] = (const void **)&o.bottom_coral;
+  slots[k++] = (const void **)&o.K_min; slots[k++] = (const void **)&o.bottom_type; slots[k++] = (const void **)&o.index_optical_depth;
+  slots[k++] = (const void **)&o.K; slots[k++] = (const void **)&o.P; slots[k++] = (const void **)&o.G; slots[k++] = (const void **)&o.X;
+  slots[k++] = (const void **)&o.converged; slots[k++] = (const void **)&o.n_evals;
+}
+
+bool use_two_classes(const ModelConst &M) {
+  if (M.n_bottoms != 3) return false; /* the default NBOTTOMS has the compile-time instantiations */
+  const char *e = getenv("PHB_ONE_CLASS");
+  return !(e && atoi(e) != 0);
+}
+
+}  // namespace
+
 extern "C" {
 
-int phb_version(void) { return 100; }
+int phb_version(void) { return 200; }
 
 const char *phb_error_string(int code) {
   switch (code) {
@@ -182,6 +251,7 @@ const char *phb_error_string(int code) {
     case PHB_ECUDA: return g_last_cuda_error.c_str();
     case PHB_ENOMEM: return "out of memory";
     case PHB_ENOFIT: return "no Jerlov fit: singular regression or slope / wavelength outside Jerlov's table";
+    case PHB_ENOPEER: return "a peer band cannot be mapped on this device (no peer access / IPC refused)";
     default: return "unknown error";
   }
 }
@@ -219,13 +289,9 @@ int64_t phb_debug_model_const(const phb_scene_desc *desc, void *out, int64_t cap
   return (int64_t)sizeof(ModelConst);
 }
 
-int phb_ctx_create(int device, phb_ctx **out) {
-  if (!out) return PHB_EINVAL;
-  int n = 0;
-  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return PHB_ENODEVICE;
-  CK(cudaSetDevice(device));
-  phb_ctx *c = new phb_ctx();
+static int ctx_init(phb_ctx *c, int device) {
   c->device = device;
+  for (int i = 0; i < 4; i++) c->ev[i] = nullptr;
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, device));
   c->n_sm = prop.multiProcessorCount;
@@ -241,9 +307,10 @@ int phb_ctx_create(int device, phb_ctx **out) {
   CK(cudaMemcpy(c->d_exp_tab, exp_tab, sizeof(exp_tab), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(c->d_log_tab, log_tab, sizeof(log_tab), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(c->d_pow_tab, pow_tab, sizeof(pow_tab), cudaMemcpyHostToDevice));
-  CK(cudaMalloc(&c->d_scalars, 4 * sizeof(int)));
+  CK(cudaMalloc(&c->d_scalars, kScalars * sizeof(int)));
   CK(cudaMalloc(&c->d_counters, 4 * sizeof(unsigned long long)));
   CK(cudaMalloc(&c->d_flops, sizeof(double)));
+  CK(cudaMalloc(&c->d_views, kMaxViews * sizeof(BandView)));
   for (int i = 0; i < 4; i++) CK(cudaEventCreate(&c->ev[i]));
   /* kHot[H_RCP_PI]: the refined reciprocal of pi exactly as this device's division fast path builds it */
   rcp_pi_kernel<<<1, 1>>>(reinterpret_cast<double *>(c->d_counters)); /* two doubles of scratch */
@@ -252,6 +319,17 @@ int phb_ctx_create(int device, phb_ctx **out) {
   CK(cudaMemcpyToSymbol(kHot, reinterpret_cast<double *>(c->d_counters) + 1, sizeof(double), H_RCP_120 * sizeof(double),
                         cudaMemcpyDeviceToDevice));
   CK(cudaDeviceSynchronize());
+  return PHB_OK;
+}
+
+int phb_ctx_create(int device, phb_ctx **out) {
+  if (!out) return PHB_EINVAL;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return PHB_ENODEVICE;
+  CK(cudaSetDevice(device));
+  phb_ctx *c = new phb_ctx();
+  const int rc = ctx_init(c, device);
+  if (rc) { phb_ctx_destroy(c); return rc; } /* nothing of a half-built context is left behind */
   *out = c;
   return PHB_OK;
 }
@@ -259,12 +337,14 @@ int phb_ctx_create(int device, phb_ctx **out) {
 void phb_ctx_destroy(phb_ctx *c) {
   if (!c) return;
   cudaSetDevice(c->device);
+  if (c->host_shard) phb_shard_destroy(c->host_shard);
   cudaFree(c->d_model); cudaFree(c->d_exp_tab); cudaFree(c->d_log_tab); cudaFree(c->d_pow_tab);
-  cudaFree(c->d_scalars); cudaFree(c->d_counters); cudaFree(c->d_flops);
+  cudaFree(c->d_scalars); cudaFree(c->d_counters); cudaFree(c->d_flops); cudaFree(c->d_views);
   c->q_shallow.release(); c->q_deep.release(); c->queue.release(); c->slabs.release();
-  c->planes.release(); c->prior.release(); c->outs.release(); c->conv.release(); c->nev.release();
+  c->planes.release(); c->prior.release(); c->outs.release(); c->nev.release();
   c->dbg_rec.release(); c->dbg_pix.release(); c->dbg_iters.release();
-  for (int i = 0; i < 4; i++) cudaEventDestroy(c->ev[i]);
+  for (int i = 0; i < 2; i++) { if (c->ring[i]) cudaFreeHost(c->ring[i]); if (c->ring_ev[i]) cudaEventDestroy(c->ring_ev[i]); }
+  for (int i = 0; i < 4; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
   delete c;
 }
 
@@ -278,20 +358,22 @@ int phb_debug_record_len(const phb_scene_desc *d) {
 
 struct LaunchGeom { int W, ctas, smem, regs; };
 
-/* Shared-memory layout, launch geometry and launch of the persistent solve kernel (pixel queue or, trials = true,
- * chains of depth-error trials). sp arrives with the work description filled in; the model, layout, slabs,
- * counters and libm tables are bound here. */
+/* Shared-memory layout, launch geometry and launch of the persistent solve kernel (pixel queues or, trials = true,
+ * chains of depth-error trials). sp arrives with the work description filled in (views, classes, trial arrays); the
+ * model, layouts, slabs, counters and libm tables are bound here. */
 static int launch_solve(phb_ctx *c, const ModelConst &M, SolveParams &sp, bool trials, cudaStream_t st, LaunchGeom *geom) {
   const int nsp = M.n_spatial == 0 ? 1 : M.n_spatial;
   const int NrMax = (2 * nsp - 1) * (2 * nsp - 1);
   sp.L = make_layout(M.SB, M.n_scenes, M.n_bottoms, NrMax);
   const long long simplex_doubles = (long long)(sp.L.nmax + 1) * sp.L.nmax;
   const long long slab_doubles = simplex_doubles + sp.L.nmax + sp.L.Tmax + (long long)((sp.L.nmax + 8) / 8 + 1) * sp.L.nmax; /* + centroid checkpoints */
-  /* kernel instantiation: compile-time substrate count for the default NBOTTOMS 3, run-time loop otherwise;
-   * compile-time (scene,band) stride 32 (up to 8 dates x 4 bands) or the maximum */
+  /* kernel instantiation: compile-time substrate count for the default NBOTTOMS 3 (followed, with two pixel classes,
+   * by the one-substrate code for the sand-only queue), run-time loop otherwise; compile-time (scene,band) stride 32
+   * (up to 8 dates x 4 bands) or the maximum */
   void (*kern)(const SolveParams) = sp.L.SBP == 32 ? solve_kernel<0, 32, false> : solve_kernel<0, kMaxSB, false>;
   if (M.n_bottoms == 3) kern = sp.L.SBP == 32 ? solve_kernel<3, 32, false> : solve_kernel<3, kMaxSB, false>; /* the default NBOTTOMS */
   if (trials) kern = sp.L.SBP == 32 ? solve_kernel<0, 32, true> : solve_kernel<0, kMaxSB, true>;
+  if (trials || M.n_bottoms != 3) sp.n_classes = 1;
   cudaFuncAttributes fa0;
   CK(cudaFuncGetAttributes(&fa0, kern));
   const int W_reg = fa0.maxThreadsPerBlock / 32;
@@ -313,6 +395,21 @@ static int launch_solve(phb_ctx *c, const ModelConst &M, SolveParams &sp, bool t
    * warps sharing a lane quarter split the columns */
   sp.L.tmem_cols = (512 / ((W + 3) / 4)) & ~1;
   if (const char *e = getenv("PHB_TMEM")) { if (atoi(e) == 0) sp.L.tmem_cols = 0; }
+  if (sp.n_classes > 1) {
+    /* the sand-only class: same CTA-shared block and the same warp stride, a smaller fixed part (n = Nr + 2 Nr + 3 Ns
+     * parameters), so more of its -- much smaller -- simplex stays in shared memory */
+    sp.L1 = make_layout(M.SB, M.n_scenes, 1, NrMax);
+    sp.L1.cta_bytes = sp.L.cta_bytes;
+    long long cache1 = (long long)sp.L.warp_bytes - sp.L1.w_simplex;
+    const long long simplex1 = (long long)(sp.L1.nmax + 1) * sp.L1.nmax * 8;
+    if (cache1 > simplex1) cache1 = simplex1;
+    if (const char *e = getenv("PHB_SIMPLEX_SMEM_BYTES")) { long long v = atoll(e); if (v >= 0 && v < cache1) cache1 = v; }
+    add_simplex_cache(sp.L1, (int)cache1);
+    sp.L1.warp_bytes = sp.L.warp_bytes;
+    sp.L1.tmem_cols = sp.L.tmem_cols;
+  } else {
+    sp.L1 = sp.L;
+  }
   int ctas = c->n_sm;
   if (const char *e = getenv("PHB_CTAS")) { int v = atoi(e); if (v >= 1) ctas = v; }
   const size_t smem = (size_t)sp.L.cta_bytes + (size_t)W * sp.L.warp_bytes;
@@ -337,9 +434,70 @@ static int launch_solve(phb_ctx *c, const ModelConst &M, SolveParams &sp, bool t
   return PHB_OK;
 }
 
+/* classification pre-pass of one band: validity, output defaults, the two work lists (and their concatenation when
+ * one generic kernel serves both classes); asynchronous on st. The band's ModelConst must be in c->d_model. */
+static int launch_classify(phb_ctx *c, const BandView &v, int row_begin, int row_end, int *q_shallow, int *q_deep, int *q_all,
+                           int *scalars, bool two_classes, cudaStream_t st) {
+  CK(cudaMemsetAsync(scalars, 0, kScalars * sizeof(int), st));
+  ClassifyParams cp;
+  cp.M = c->d_model; cp.planes = v.planes; cp.prior = v.prior;
+  cp.row_begin = row_begin; cp.row_end = row_end;
+  cp.queue_shallow = q_shallow; cp.queue_deep = q_deep;
+  cp.n_shallow = scalars + 0; cp.n_deep = scalars + 1;
+  cp.out = v.out;
+  classify_kernel<<<c->n_sm * 8, 256, 0, st>>>(cp);
+  if (!two_classes)
+    concat_queue_kernel<<<c->n_sm * 4, 256, 0, st>>>(q_shallow, q_deep, scalars + 0, scalars + 1, q_all, scalars + 2);
+  CK(cudaGetLastError());
+  return PHB_OK;
+}
+
+/* the queue members of a band's view for the one- or two-class kernels */
+static void bind_queues(BandView &v, int *q_shallow, int *q_deep, int *q_all, int *scalars, bool two_classes) {
+  if (two_classes) {
+    v.queue[0] = q_shallow; v.n_queue[0] = scalars + 0; v.head[0] = scalars + 3;
+    v.queue[1] = q_deep; v.n_queue[1] = scalars + 1; v.head[1] = scalars + 4;
+  } else {
+    v.queue[0] = q_all; v.n_queue[0] = scalars + 2; v.head[0] = scalars + 3;
+    v.queue[1] = q_all; v.n_queue[1] = scalars + 5; v.head[1] = scalars + 4; /* scalars[5] stays 0: an empty queue */
+  }
+}
+
+/* solve over a list of views (host copies; [0] = the device's own band) + counters read-back */
+static int run_solve(phb_ctx *c, const ModelConst &M, const BandView *views, int n_views, bool two_classes,
+                     double *d_rec, int *d_pix, int *d_iters, int reclen, long long dbg_cap, cudaStream_t st,
+                     cudaEvent_t e_begin, cudaEvent_t e_end, phb_stats *stats) {
+  if (n_views < 1 || n_views > kMaxViews) return PHB_EINVAL;
+  CK(cudaMemcpyAsync(c->d_views, views, (size_t)n_views * sizeof(BandView), cudaMemcpyHostToDevice, st));
+  CK(cudaMemsetAsync(c->d_counters, 0, 4 * sizeof(unsigned long long), st));
+  CK(cudaMemsetAsync(c->d_flops, 0, sizeof(double), st));
+  SolveParams sp;
+  memset(&sp, 0, sizeof(sp));
+  sp.views = c->d_views; sp.n_views = n_views; sp.n_classes = two_classes ? 2 : 1;
+  sp.dbg_rec = d_rec; sp.dbg_pix = d_pix; sp.dbg_iters = d_iters; sp.reclen = reclen; sp.dbg_capacity = dbg_cap;
+  LaunchGeom geom;
+  CK(cudaEventRecord(e_begin, st));
+  int rc = launch_solve(c, M, sp, false, st, &geom);
+  if (rc) return rc;
+  CK(cudaEventRecord(e_end, st));
+  if (stats) {
+    unsigned long long cnt[4];
+    double fl;
+    CK(cudaMemcpyAsync(cnt, c->d_counters, sizeof(cnt), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&fl, c->d_flops, sizeof(fl), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    stats->n_valid = (int64_t)cnt[3];
+    stats->n_evals = (int64_t)cnt[0]; stats->n_iters = (int64_t)cnt[1]; stats->n_converged = (int64_t)cnt[2];
+    stats->alg_flops = fl;
+    CK(cudaEventElapsedTime(&stats->ms_solve, e_begin, e_end));
+    stats->warps_per_cta = geom.W; stats->ctas = geom.ctas; stats->smem_bytes = geom.smem;
+    stats->regs = geom.regs;
+  }
+  return PHB_OK;
+}
+
 static int invert_device_impl(phb_ctx *c, const phb_scene_desc *desc, const float *d_planes, const float *d_prior,
-                              int row_begin, int row_end, const phb_outputs *d_out, cudaStream_t st, phb_stats *stats,
-                              double *d_rec, int *d_pix, int *d_iters, long long dbg_cap) {
+                              int row_begin, int row_end, const phb_outputs *d_out, cudaStream_t st, phb_stats *stats) {
   if (!c || !d_planes || !d_out) return PHB_EINVAL;
   int rc = validate(desc);
   if (rc) return rc;
@@ -349,169 +507,482 @@ static int invert_device_impl(phb_ctx *c, const phb_scene_desc *desc, const floa
   build_model(desc, &M);
   CK(cudaMemcpyAsync(c->d_model, &M, sizeof(M), cudaMemcpyHostToDevice, st));
   const size_t npx = (size_t)(row_end - row_begin) * desc->ncols;
-  CK(c->q_shallow.ensure(npx)); CK(c->q_deep.ensure(npx)); CK(c->queue.ensure(npx));
-  CK(cudaMemsetAsync(c->d_scalars, 0, 4 * sizeof(int), st));
-  CK(cudaMemsetAsync(c->d_counters, 0, 4 * sizeof(unsigned long long), st));
-  CK(cudaMemsetAsync(c->d_flops, 0, sizeof(double), st));
-
-  /* classification pre-pass */
-  ClassifyParams cp;
-  cp.M = c->d_model; cp.planes = d_planes; cp.prior = desc->prior_present ? d_prior : nullptr;
-  cp.row_begin = row_begin; cp.row_end = row_end;
-  cp.queue_shallow = c->q_shallow.p; cp.queue_deep = c->q_deep.p;
-  cp.n_shallow = c->d_scalars + 0; cp.n_deep = c->d_scalars + 1;
-  cp.out = *d_out;
+  const bool two = use_two_classes(M);
+  CK(c->q_shallow.ensure(npx)); CK(c->q_deep.ensure(npx));
+  if (!two) CK(c->queue.ensure(npx));
+  BandView v;
+  memset(&v, 0, sizeof(v));
+  v.planes = d_planes; v.prior = desc->prior_present ? d_prior : nullptr; v.nrows = desc->nrows; v.out = *d_out;
+  bind_queues(v, c->q_shallow.p, c->q_deep.p, c->queue.p, c->d_scalars, two);
   CK(cudaEventRecord(c->ev[0], st));
-  classify_kernel<<<c->n_sm * 8, 256, 0, st>>>(cp);
-  concat_queue_kernel<<<c->n_sm * 4, 256, 0, st>>>(c->q_shallow.p, c->q_deep.p, c->d_scalars + 0, c->d_scalars + 1,
-                                                    c->queue.p, c->d_scalars + 2);
-  CK(cudaEventRecord(c->ev[1], st));
-  CK(cudaGetLastError());
-
-  /* solve */
-  SolveParams sp;
-  memset(&sp, 0, sizeof(sp));
-  sp.planes = d_planes; sp.prior = cp.prior;
-  sp.queue = c->queue.p; sp.n_queue = c->d_scalars + 2; sp.head = c->d_scalars + 3;
-  sp.out = *d_out;
-  sp.dbg_rec = d_rec; sp.dbg_pix = d_pix; sp.dbg_iters = d_iters; sp.reclen = phb_debug_record_len(desc);
-  sp.dbg_capacity = dbg_cap;
-  LaunchGeom geom;
-  CK(cudaEventRecord(c->ev[2], st));
-  rc = launch_solve(c, M, sp, false, st, &geom);
+  rc = launch_classify(c, v, row_begin, row_end, c->q_shallow.p, c->q_deep.p, c->queue.p, c->d_scalars, two, st);
   if (rc) return rc;
-  CK(cudaEventRecord(c->ev[3], st));
-
+  CK(cudaEventRecord(c->ev[1], st));
+  phb_stats local;
+  memset(&local, 0, sizeof(local));
+  rc = run_solve(c, M, &v, 1, two, nullptr, nullptr, nullptr, phb_debug_record_len(desc), 0, st, c->ev[2], c->ev[3],
+                 stats ? &local : nullptr);
+  if (rc) return rc;
   if (stats) {
-    unsigned long long cnt[4];
-    int sc[4];
-    double fl;
-    CK(cudaMemcpyAsync(cnt, c->d_counters, sizeof(cnt), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(sc, c->d_scalars, sizeof(sc), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(&fl, c->d_flops, sizeof(fl), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    memset(stats, 0, sizeof(*stats));
-    stats->n_valid = sc[2]; stats->n_shallow = sc[0];
-    stats->n_evals = (int64_t)cnt[0]; stats->n_iters = (int64_t)cnt[1]; stats->n_converged = (int64_t)cnt[2];
-    stats->alg_flops = fl;
-    CK(cudaEventElapsedTime(&stats->ms_classify, c->ev[0], c->ev[1]));
-    CK(cudaEventElapsedTime(&stats->ms_solve, c->ev[2], c->ev[3]));
-    stats->warps_per_cta = geom.W; stats->ctas = geom.ctas; stats->smem_bytes = geom.smem;
-    stats->regs = geom.regs;
+    int sc[kScalars];
+    CK(cudaMemcpy(sc, c->d_scalars, sizeof(sc), cudaMemcpyDeviceToHost));
+    local.n_shallow = sc[0];
+    CK(cudaEventElapsedTime(&local.ms_classify, c->ev[0], c->ev[1]));
+    *stats = local;
   }
   return PHB_OK;
 }
 
 int phb_invert_device(phb_ctx *ctx, const phb_scene_desc *desc, const float *d_planes, const float *d_prior,
                       int row_begin, int row_end, const phb_outputs *d_out, void *stream, phb_stats *stats) {
-  return invert_device_impl(ctx, desc, d_planes, d_prior, row_begin, row_end, d_out, (cudaStream_t)stream, stats,
-                            nullptr, nullptr, nullptr, 0);
+  return invert_device_impl(ctx, desc, d_planes, d_prior, row_begin, row_end, d_out, (cudaStream_t)stream, stats);
 }
 
-/* Where the raster of `desc` sits inside the caller's host rasters: row `row0` of planes whose per-plane stride
- * (for the stacked K / P / G / X outputs) is `plane_px` cells. {0, 0} = the host rasters ARE the raster of desc. */
-struct HostView { long long row0; size_t plane_px; };
+/* ---- row bands shareable between devices ------------------------------------------------------------------- */
 
-static int invert_host_impl(phb_ctx *c, const phb_scene_desc *desc, const float *const *h_planes, const float *h_prior,
-                            int row_begin, int row_end, const phb_outputs *h_out, phb_stats *stats, double *rec,
-                            int32_t *pix, int32_t *iters, int64_t capacity, HostView view = HostView{0, 0}) {
-  if (!c || !h_planes || !h_out) return PHB_EINVAL;
+int phb_shard_create(phb_ctx *c, const phb_scene_desc *desc, int row_begin, int row_end, int scene_planes, phb_shard **out) {
+  if (!c || !out) return PHB_EINVAL;
+  int rc = validate(desc);
+  if (rc) return rc;
+  if (row_begin < 0 || row_end > desc->nrows || row_begin > row_end) return PHB_EINVAL;
+  CK(cudaSetDevice(c->device));
+  phb_shard *S = new phb_shard();
+  S->ctx = c; S->desc = *desc; S->row_begin = row_begin; S->row_end = row_end; S->scene_planes = scene_planes ? 1 : 0;
+  build_model(desc, &S->M);
+  S->SB = S->M.SB; S->mb = S->M.max_bands; S->Ns = S->M.n_scenes;
+  S->two_classes = use_two_classes(S->M) ? 1 : 0;
+  const size_t px = (size_t)desc->nrows * desc->ncols;
+  const size_t own = (size_t)(row_end - row_begin) * desc->ncols;
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t at = o; o += (bytes + 255) & ~(size_t)255; return at; };
+  const size_t o_planes = take(px * S->SB * 4), o_prior = take(px * 4);
+  size_t o_out[9];
+  for (int k = 0; k < 9; k++) o_out[k] = take(px * 4);
+  const size_t o_K = take(scene_planes ? px * 4 * S->Ns * S->mb : 0), o_P = take(scene_planes ? px * 4 * S->Ns : 0),
+               o_G = take(scene_planes ? px * 4 * S->Ns : 0), o_X = take(scene_planes ? px * 4 * S->Ns : 0);
+  const size_t o_conv = take(px), o_nev = take(px * 4);
+  const size_t o_qs = take(own * 4 + 4), o_qd = take(own * 4 + 4), o_qa = take(S->two_classes ? 4 : own * 4 + 4), o_sc = take(kScalars * 4);
+  S->bytes = o;
+  cudaError_t e = cudaMalloc(&S->base, S->bytes);
+  if (e != cudaSuccess) { g_last_cuda_error = std::string("cudaMalloc(band): ") + cudaGetErrorString(e); delete S; return e == cudaErrorMemoryAllocation ? PHB_ENOMEM : PHB_ECUDA; }
+  unsigned char *b = S->base;
+  BandView &v = S->view;
+  memset(&v, 0, sizeof(v));
+  v.planes = reinterpret_cast<float *>(b + o_planes);
+  v.prior = desc->prior_present ? reinterpret_cast<float *>(b + o_prior) : nullptr;
+  v.nrows = desc->nrows;
+  float **slots[9] = {&v.out.depth, &v.out.model_error, &v.out.bottom_albedo, &v.out.bottom_sand, &v.out.bottom_seagrass,
+                      &v.out.bottom_coral, &v.out.K_min, &v.out.bottom_type, &v.out.index_optical_depth};
+  for (int k = 0; k < 9; k++) *slots[k] = reinterpret_cast<float *>(b + o_out[k]);
+  if (scene_planes) {
+    v.out.K = reinterpret_cast<float *>(b + o_K); v.out.P = reinterpret_cast<float *>(b + o_P);
+    v.out.G = reinterpret_cast<float *>(b + o_G); v.out.X = reinterpret_cast<float *>(b + o_X);
+  }
+  v.out.converged = b + o_conv; v.out.n_evals = reinterpret_cast<int32_t *>(b + o_nev);
+  S->q_shallow = reinterpret_cast<int *>(b + o_qs); S->q_deep = reinterpret_cast<int *>(b + o_qd);
+  S->q_all = reinterpret_cast<int *>(b + o_qa); S->scalars = reinterpret_cast<int *>(b + o_sc);
+  bind_queues(v, S->q_shallow, S->q_deep, S->q_all, S->scalars, S->two_classes != 0);
+  for (int k = 0; k < 4; k++) {
+    e = cudaEventCreate(&S->ev[k]);
+    if (e != cudaSuccess) { g_last_cuda_error = std::string("cudaEventCreate: ") + cudaGetErrorString(e); phb_shard_destroy(S); return PHB_ECUDA; }
+  }
+  e = cudaMemset(S->scalars, 0, kScalars * sizeof(int));
+  if (e != cudaSuccess) { g_last_cuda_error = std::string("cudaMemset: ") + cudaGetErrorString(e); phb_shard_destroy(S); return PHB_ECUDA; }
+  *out = S;
+  return PHB_OK;
+}
+
+void phb_shard_destroy(phb_shard *S) {
+  if (!S) return;
+  cudaSetDevice(S->ctx->device);
+  for (auto &m : S->mapped)
+    if (m.ipc) cudaIpcCloseMemHandle(m.ptr);
+  if (S->base) cudaFree(S->base);
+  for (cudaEvent_t x : S->ev) if (x) cudaEventDestroy(x);
+  delete S;
+}
+
+int phb_shard_buffers(phb_shard *S, float **d_planes, float **d_prior, phb_outputs *d_out) {
+  if (!S) return PHB_EINVAL;
+  if (d_planes) *d_planes = const_cast<float *>(S->view.planes);
+  if (d_prior) *d_prior = const_cast<float *>(S->view.prior);
+  if (d_out) *d_out = S->view.out;
+  return PHB_OK;
+}
+
+int phb_shard_export(phb_shard *S, phb_shard_handle *h) {
+  if (!S || !h) return PHB_EINVAL;
+  CK(cudaSetDevice(S->ctx->device));
+  memset(h, 0, sizeof(*h));
+  HandleData d;
+  memset(&d, 0, sizeof(d));
+  d.magic = kHandleMagic; d.device = S->ctx->device; d.pid = (int64_t)getpid();
+  d.base = (uint64_t)(uintptr_t)S->base; d.bytes = S->bytes;
+  d.nrows = S->desc.nrows; d.ncols = S->desc.ncols; d.two_classes = S->two_classes;
+  d.ipc_ok = cudaIpcGetMemHandle(&d.ipc, S->base) == cudaSuccess ? 1 : 0; /* only another PROCESS needs it */
+  if (!d.ipc_ok) (void)cudaGetLastError();
+  BandView v = S->view;
+  const void **slots[23];
+  view_pointers(v, slots);
+  for (int k = 0; k < 23; k++) d.off[k] = *slots[k] ? (uint64_t)((const unsigned char *)*slots[k] - S->base) : kNullOff;
+  memcpy(h->bytes, &d, sizeof(d));
+  return PHB_OK;
+}
+
+/* a peer's band in THIS device's address space */
+static int map_peer(phb_shard *S, const phb_shard_handle *h, BandView *out) {
+  HandleData d;
+  memcpy(&d, h->bytes, sizeof(d));
+  if (d.magic != kHandleMagic || d.ncols != S->desc.ncols || d.two_classes != S->two_classes) return PHB_EINVAL;
+  unsigned char *ptr = nullptr;
+  for (auto &m : S->mapped)
+    if (m.pid == d.pid && m.base == d.base) ptr = m.ptr;
+  if (!ptr) {
+    const int me = S->ctx->device;
+    if (d.pid == (int64_t)getpid()) { /* same process: the owner's pointer, peer access between the two devices */
+      if (d.device != me) {
+        int can = 0;
+        if (cudaDeviceCanAccessPeer(&can, me, d.device) != cudaSuccess || !can) { (void)cudaGetLastError(); return PHB_ENOPEER; }
+        cudaError_t e = cudaDeviceEnablePeerAccess(d.device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { (void)cudaGetLastError(); return PHB_ENOPEER; }
+        (void)cudaGetLastError();
+      }
+      ptr = reinterpret_cast<unsigned char *>((uintptr_t)d.base);
+      S->mapped.push_back({d.pid, d.base, ptr, false});
+    } else { /* another process: CUDA IPC (enables peer access as needed) */
+      if (!d.ipc_ok) return PHB_ENOPEER;
+      void *p = nullptr;
+      cudaError_t e = cudaIpcOpenMemHandle(&p, d.ipc, cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) {
+        g_last_cuda_error = std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e);
+        (void)cudaGetLastError();
+        return PHB_ENOPEER;
+      }
+      ptr = static_cast<unsigned char *>(p);
+      S->mapped.push_back({d.pid, d.base, ptr, true});
+    }
+  }
+  BandView v;
+  memset(&v, 0, sizeof(v));
+  const void **slots[23];
+  view_pointers(v, slots);
+  for (int k = 0; k < 23; k++) *slots[k] = d.off[k] == kNullOff ? nullptr : (const void *)(ptr + d.off[k]);
+  v.nrows = d.nrows;
+  *out = v;
+  return PHB_OK;
+}
+
+int phb_shard_prepare(phb_shard *S, void *stream) {
+  if (!S) return PHB_EINVAL;
+  phb_ctx *c = S->ctx;
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaSetDevice(c->device));
+  CK(cudaMemcpyAsync(c->d_model, &S->M, sizeof(ModelConst), cudaMemcpyHostToDevice, st));
+  CK(cudaEventRecord(S->ev[0], st));
+  if (S->row_end > S->row_begin) {
+    int rc = launch_classify(c, S->view, S->row_begin, S->row_end, S->q_shallow, S->q_deep, S->q_all, S->scalars,
+                             S->two_classes != 0, st);
+    if (rc) return rc;
+  } else {
+    CK(cudaMemsetAsync(S->scalars, 0, kScalars * sizeof(int), st));
+  }
+  CK(cudaEventRecord(S->ev[1], st));
+  return PHB_OK;
+}
+
+int64_t phb_shard_valid(phb_shard *S) {
+  if (!S) return -1;
+  int sc[kScalars];
+  if (cudaSetDevice(S->ctx->device) != cudaSuccess) return -1;
+  if (cudaMemcpy(sc, S->scalars, sizeof(sc), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  return (int64_t)sc[0] + sc[1];
+}
+
+int phb_shard_solve(phb_shard *S, const phb_shard_handle *peers, int n_peers, void *stream, phb_stats *stats) {
+  if (!S || n_peers < 0 || n_peers + 1 > kMaxViews || (n_peers > 0 && !peers)) return PHB_EINVAL;
+  phb_ctx *c = S->ctx;
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaSetDevice(c->device));
+  std::vector<BandView> views(1 + n_peers);
+  views[0] = S->view;
+  for (int k = 0; k < n_peers; k++) {
+    int rc = map_peer(S, &peers[k], &views[1 + k]);
+    if (rc) return rc;
+  }
+  /* the model of THIS band (prepare of another band on the same context may have replaced it) */
+  CK(cudaMemcpyAsync(c->d_model, &S->M, sizeof(ModelConst), cudaMemcpyHostToDevice, st));
+  phb_stats local;
+  memset(&local, 0, sizeof(local));
+  int rc = run_solve(c, S->M, views.data(), 1 + n_peers, S->two_classes != 0, S->dbg_rec, S->dbg_pix, S->dbg_iters,
+                     phb_debug_record_len(&S->desc), S->dbg_cap, st, S->ev[2], S->ev[3], stats ? &local : nullptr);
+  if (rc) return rc;
+  if (stats) {
+    int sc[kScalars];
+    CK(cudaMemcpy(sc, S->scalars, sizeof(sc), cudaMemcpyDeviceToHost));
+    local.n_shallow = sc[0];
+    CK(cudaEventElapsedTime(&local.ms_classify, S->ev[0], S->ev[1]));
+    *stats = local;
+  }
+  return PHB_OK;
+}
+
+/* ---- host entry points: caller's rasters in host memory ------------------------------------------------------ */
+
+}  /* extern "C" */
+
+namespace {
+
+/* read access to the caller's host rasters by row: contiguous planes or the reference's row pointers */
+struct RowSrc {
+  const float *const *planes = nullptr;            /* [SB], each [rows][ncols] */
+  const float *const *const *plane_rows = nullptr; /* [SB][rows] */
+  const float *prior = nullptr;
+  const float *const *prior_rows = nullptr;
+  int ncols = 0;
+  const float *row(int g, long long r) const { return plane_rows ? plane_rows[g][r] : planes[g] + (size_t)r * ncols; }
+  const float *prow(long long r) const { return prior_rows ? prior_rows[r] : prior + (size_t)r * ncols; }
+  bool has_prior() const { return prior != nullptr || prior_rows != nullptr; }
+};
+
+/* write access to the caller's result rasters by row */
+struct RowDst {
+  const phb_outputs *flat = nullptr;
+  const phb_row_outputs *rows = nullptr;
+  size_t plane_px = 0; /* cells per plane of the caller's stacked K / P / G / X planes (flat form) */
+  int ncols = 0;
+  /* scalar grid k (0..8) */
+  float *scalar(int k, long long r) const {
+    if (rows) {
+      float *const *g[9] = {rows->depth, rows->model_error, rows->bottom_albedo, rows->bottom_sand, rows->bottom_seagrass,
+                            rows->bottom_coral, rows->K_min, rows->bottom_type, rows->index_optical_depth};
+      return g[k] ? g[k][r] : nullptr;
+    }
+    float *g[9] = {flat->depth, flat->model_error, flat->bottom_albedo, flat->bottom_sand, flat->bottom_seagrass,
+                   flat->bottom_coral, flat->K_min, flat->bottom_type, flat->index_optical_depth};
+    return g[k] ? g[k] + (size_t)r * ncols : nullptr;
+  }
+  /* stacked planes: which = 0 K, 1 P, 2 G, 3 X; q = plane within the stack */
+  float *stacked(int which, int q, long long r) const {
+    if (rows) {
+      float *const *const *g[4] = {rows->K, rows->P, rows->G, rows->X};
+      return g[which] ? g[which][q][r] : nullptr;
+    }
+    float *g[4] = {flat->K, flat->P, flat->G, flat->X};
+    return g[which] ? g[which] + (size_t)q * plane_px + (size_t)r * ncols : nullptr;
+  }
+  bool wants_stacked() const { return rows ? (rows->K || rows->P || rows->G || rows->X) : (flat->K || flat->P || flat->G || flat->X); }
+};
+
+int ring_open(phb_ctx *c) {
+  for (int i = 0; i < 2; i++) {
+    if (!c->ring[i]) CK(cudaHostAlloc(&c->ring[i], kRingBytes, cudaHostAllocDefault));
+    if (!c->ring_ev[i]) CK(cudaEventCreateWithFlags(&c->ring_ev[i], cudaEventDisableTiming));
+  }
+  return PHB_OK;
+}
+
+/* host rows -> device plane through the pinned ring: rows [r0, r1) of one host raster (row accessor) to dst */
+template <class RowFn>
+int ring_upload(phb_ctx *c, int &slot, RowFn row_of, long long r0, long long r1, int ncols, float *dst, cudaStream_t st) {
+  const long long rows_per = (long long)(kRingBytes / ((size_t)ncols * 4));
+  if (rows_per < 1) return PHB_EINVAL;
+  for (long long a = r0; a < r1; a += rows_per) {
+    const long long b = a + rows_per < r1 ? a + rows_per : r1;
+    CK(cudaEventSynchronize(c->ring_ev[slot])); /* the copy that last used this slot has drained */
+    float *buf = c->ring[slot];
+    for (long long r = a; r < b; r++) memcpy(buf + (size_t)(r - a) * ncols, row_of(r), (size_t)ncols * 4);
+    CK(cudaMemcpyAsync(dst + (size_t)(a - r0) * ncols, buf, (size_t)(b - a) * ncols * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaEventRecord(c->ring_ev[slot], st));
+    slot ^= 1;
+  }
+  return PHB_OK;
+}
+
+/* device plane rows -> host rows through the pinned ring, double buffered: while chunk k is in flight chunk k-1 is
+ * scattered into the caller's rows */
+template <class RowFn>
+int ring_download(phb_ctx *c, RowFn row_of, long long r0, long long r1, int ncols, const void *src, size_t elem, cudaStream_t st) {
+  const long long rows_per = (long long)(kRingBytes / ((size_t)ncols * elem));
+  if (rows_per < 1) return PHB_EINVAL;
+  long long pa[2] = {0, 0}, pb[2] = {0, 0};
+  bool pending[2] = {false, false};
+  int slot = 0;
+  auto drain = [&](int s) -> int {
+    if (!pending[s]) return PHB_OK;
+    CK(cudaEventSynchronize(c->ring_ev[s]));
+    const unsigned char *buf = reinterpret_cast<const unsigned char *>(c->ring[s]);
+    for (long long r = pa[s]; r < pb[s]; r++) memcpy(row_of(r), buf + (size_t)(r - pa[s]) * ncols * elem, (size_t)ncols * elem);
+    pending[s] = false;
+    return PHB_OK;
+  };
+  for (long long a = r0; a < r1; a += rows_per) {
+    const long long b = a + rows_per < r1 ? a + rows_per : r1;
+    int rc = drain(slot);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(c->ring[slot], static_cast<const unsigned char *>(src) + (size_t)(a - r0) * ncols * elem,
+                       (size_t)(b - a) * ncols * elem, cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(c->ring_ev[slot], st));
+    pa[slot] = a; pb[slot] = b; pending[slot] = true;
+    slot ^= 1;
+  }
+  int rc = drain(slot);
+  if (rc) return rc;
+  return drain(slot ^ 1);
+}
+
+/* the band of a host entry point: kept in the context between calls while its shape stays the same */
+int host_band(phb_ctx *c, const phb_scene_desc *dd, int row_begin, int row_end, bool scene_planes, phb_shard **out) {
+  phb_shard *S = c->host_shard;
+  if (S && (memcmp(&S->desc, dd, sizeof(*dd)) != 0 || S->row_begin != row_begin || S->row_end != row_end ||
+            S->scene_planes != (scene_planes ? 1 : 0) || S->two_classes != (use_two_classes(S->M) ? 1 : 0))) {
+    phb_shard_destroy(S);
+    S = c->host_shard = nullptr;
+  }
+  if (!S) {
+    int rc = phb_shard_create(c, dd, row_begin, row_end, scene_planes ? 1 : 0, &S);
+    if (rc) return rc;
+    c->host_shard = S;
+  }
+  *out = S;
+  return PHB_OK;
+}
+
+/* rows [w0, w1) of the caller's rasters -> the band's device rasters */
+int band_upload(phb_shard *S, const RowSrc &src, long long w0, cudaStream_t st) {
+  phb_ctx *c = S->ctx;
+  int rc = ring_open(c);
+  if (rc) return rc;
+  const int nr = S->desc.nrows, nc = S->desc.ncols;
+  const size_t px = (size_t)nr * nc;
+  int slot = 0;
+  for (int g = 0; g < S->SB; g++) {
+    rc = ring_upload(c, slot, [&](long long r) { return src.row(g, r); }, w0, w0 + nr, nc,
+                     const_cast<float *>(S->view.planes) + g * px, st);
+    if (rc) return rc;
+  }
+  if (S->view.prior) {
+    rc = ring_upload(c, slot, [&](long long r) { return src.prow(r); }, w0, w0 + nr, nc, const_cast<float *>(S->view.prior), st);
+    if (rc) return rc;
+  }
+  return PHB_OK;
+}
+
+/* the band's own rows of the result planes -> the caller's rasters (scene rows w0 + [row_begin, row_end)) */
+int band_download(phb_shard *S, const RowDst &dst, const phb_outputs *flat_flags, long long w0, cudaStream_t st) {
+  phb_ctx *c = S->ctx;
+  const int nc = S->desc.ncols;
+  const size_t px = (size_t)S->desc.nrows * nc, a = (size_t)S->row_begin * nc;
+  const long long r0 = w0 + S->row_begin, r1 = w0 + S->row_end;
+  const phb_outputs &d = S->view.out;
+  const float *dev9[9] = {d.depth, d.model_error, d.bottom_albedo, d.bottom_sand, d.bottom_seagrass, d.bottom_coral,
+                          d.K_min, d.bottom_type, d.index_optical_depth};
+  int rc;
+  for (int k = 0; k < 9; k++) {
+    if (!dst.scalar(k, r0)) continue;
+    rc = ring_download(c, [&](long long r) { return (void *)dst.scalar(k, r); }, r0, r1, nc, dev9[k] + a, 4, st);
+    if (rc) return rc;
+  }
+  if (S->scene_planes) {
+    const float *devs[4] = {d.K, d.P, d.G, d.X};
+    const int count[4] = {S->Ns * S->mb, S->Ns, S->Ns, S->Ns};
+    for (int w = 0; w < 4; w++)
+      for (int q = 0; q < count[w]; q++) {
+        if (!dst.stacked(w, q, r0)) continue;
+        rc = ring_download(c, [&](long long r) { return (void *)dst.stacked(w, q, r); }, r0, r1, nc, devs[w] + (size_t)q * px + a, 4, st);
+        if (rc) return rc;
+      }
+  }
+  if (flat_flags && flat_flags->converged) {
+    uint8_t *h = flat_flags->converged;
+    rc = ring_download(c, [&](long long r) { return (void *)(h + (size_t)r * nc); }, r0, r1, nc, d.converged + a, 1, st);
+    if (rc) return rc;
+  }
+  if (flat_flags && flat_flags->n_evals) {
+    int32_t *h = flat_flags->n_evals;
+    rc = ring_download(c, [&](long long r) { return (void *)(h + (size_t)r * nc); }, r0, r1, nc, d.n_evals + a, 4, st);
+    if (rc) return rc;
+  }
+  return PHB_OK;
+}
+
+int scene_bands(const phb_scene_desc *d) {
+  int SB = 0;
+  for (int s = 0; s < d->n_scenes; s++) SB += d->n_bands[s];
+  return SB;
+}
+
+/* one device, whole raster (or a row window of it): upload, classify, solve, download */
+int invert_host_one(phb_ctx *c, const phb_scene_desc *desc, const RowSrc &src, int row_begin, int row_end, const RowDst &dst,
+                    const phb_outputs *flat_flags, phb_stats *stats, double *rec, int32_t *pix, int32_t *iters, int64_t capacity) {
+  if (!c) return PHB_EINVAL;
   int rc = validate(desc);
   if (rc) return rc;
   if (row_begin < 0 || row_end > desc->nrows || row_begin >= row_end) return PHB_EINVAL;
   CK(cudaSetDevice(c->device));
-  int SB = 0, mb = 0;
-  for (int s = 0; s < desc->n_scenes; s++) { SB += desc->n_bands[s]; mb = desc->n_bands[s] > mb ? desc->n_bands[s] : mb; }
-  const size_t px = (size_t)desc->nrows * desc->ncols;
-  const size_t hpx = view.plane_px ? view.plane_px : px;          /* host stride of the stacked output planes */
-  const size_t h0 = (size_t)view.row0 * (size_t)desc->ncols;      /* first cell of this raster in the host planes */
-  const int Ns = desc->n_scenes;
   cudaStream_t st = 0;
+  phb_scene_desc dd = *desc;
+  dd.prior_present = (desc->prior_present && src.has_prior()) ? 1 : 0;
+  phb_shard *S = nullptr;
+  rc = host_band(c, &dd, row_begin, row_end, dst.wants_stacked(), &S);
+  if (rc) return rc;
   struct Events { /* released on every return path */
     cudaEvent_t e[4] = {nullptr, nullptr, nullptr, nullptr};
     ~Events() { for (cudaEvent_t x : e) if (x) cudaEventDestroy(x); }
   } evs;
   for (int k = 0; k < 4; k++) CK(cudaEventCreate(&evs.e[k]));
-  const cudaEvent_t e0 = evs.e[0], e1 = evs.e[1], e2 = evs.e[2], e3 = evs.e[3];
-  CK(c->planes.ensure(px * SB));
-  CK(cudaEventRecord(e0, st));
-  for (int g = 0; g < SB; g++)
-    CK(cudaMemcpyAsync(c->planes.p + g * px, h_planes[g] + h0, px * sizeof(float), cudaMemcpyHostToDevice, st));
-  const bool use_prior = desc->prior_present && h_prior;
-  if (use_prior) {
-    CK(c->prior.ensure(px));
-    CK(cudaMemcpyAsync(c->prior.p, h_prior + h0, px * sizeof(float), cudaMemcpyHostToDevice, st));
-  }
-  CK(cudaEventRecord(e1, st));
-  /* device output planes: 9 scalar grids, K, P, G, X */
-  const size_t n_out_planes = 9 + (size_t)Ns * mb + 3 * (size_t)Ns;
-  CK(c->outs.ensure(n_out_planes * px));
-  CK(c->conv.ensure(px)); CK(c->nev.ensure(px));
-  phb_outputs d;
-  float *o = c->outs.p;
-  float **slots[9] = {&d.depth, &d.model_error, &d.bottom_albedo, &d.bottom_sand, &d.bottom_seagrass, &d.bottom_coral,
-                      &d.K_min, &d.bottom_type, &d.index_optical_depth};
-  float *const hslots[9] = {h_out->depth, h_out->model_error, h_out->bottom_albedo, h_out->bottom_sand,
-                            h_out->bottom_seagrass, h_out->bottom_coral, h_out->K_min, h_out->bottom_type,
-                            h_out->index_optical_depth};
-  for (int k = 0; k < 9; k++) { *slots[k] = hslots[k] ? o : nullptr; o += px; }
-  d.K = h_out->K ? o : nullptr; o += (size_t)Ns * mb * px;
-  d.P = h_out->P ? o : nullptr; o += (size_t)Ns * px;
-  d.G = h_out->G ? o : nullptr; o += (size_t)Ns * px;
-  d.X = h_out->X ? o : nullptr; o += (size_t)Ns * px;
-  d.converged = h_out->converged ? c->conv.p : nullptr;
-  d.n_evals = h_out->n_evals ? c->nev.p : nullptr;
-  double *d_rec = nullptr; int *d_pix = nullptr, *d_it = nullptr;
+  CK(cudaEventRecord(evs.e[0], st));
+  rc = band_upload(S, src, 0, st);
+  if (rc) return rc;
+  CK(cudaEventRecord(evs.e[1], st));
   const int reclen = phb_debug_record_len(desc);
+  S->dbg_rec = nullptr; S->dbg_pix = nullptr; S->dbg_iters = nullptr; S->dbg_cap = 0;
   if (rec && capacity > 0) {
     CK(c->dbg_rec.ensure((size_t)capacity * reclen)); CK(c->dbg_pix.ensure(capacity)); CK(c->dbg_iters.ensure(3 * capacity));
     CK(cudaMemsetAsync(c->dbg_pix.p, 0xff, capacity * sizeof(int), st));
-    d_rec = c->dbg_rec.p; d_pix = c->dbg_pix.p; d_it = c->dbg_iters.p;
+    S->dbg_rec = c->dbg_rec.p; S->dbg_pix = c->dbg_pix.p; S->dbg_iters = c->dbg_iters.p; S->dbg_cap = capacity;
   }
-  phb_stats local;
-  phb_scene_desc dd = *desc;
-  dd.prior_present = use_prior ? 1 : 0;
-  rc = invert_device_impl(c, &dd, c->planes.p, use_prior ? c->prior.p : nullptr, row_begin, row_end, &d, st, &local, d_rec,
-                          d_pix, d_it, capacity);
+  rc = phb_shard_prepare(S, st);
   if (rc) return rc;
-  /* copy back only the rows that were inverted */
-  const size_t a = (size_t)row_begin * desc->ncols, nb = (size_t)(row_end - row_begin) * desc->ncols;
-  CK(cudaEventRecord(e2, st));
-  for (int k = 0; k < 9; k++)
-    if (hslots[k]) CK(cudaMemcpyAsync(hslots[k] + h0 + a, *slots[k] + a, nb * sizeof(float), cudaMemcpyDeviceToHost, st));
-  if (h_out->K)
-    for (int q = 0; q < Ns * mb; q++)
-      CK(cudaMemcpyAsync(h_out->K + q * hpx + h0 + a, d.K + q * px + a, nb * sizeof(float), cudaMemcpyDeviceToHost, st));
-  float *const hpgx[3] = {h_out->P, h_out->G, h_out->X};
-  float *const dpgx[3] = {d.P, d.G, d.X};
-  for (int v = 0; v < 3; v++)
-    if (hpgx[v])
-      for (int s = 0; s < Ns; s++)
-        CK(cudaMemcpyAsync(hpgx[v] + s * hpx + h0 + a, dpgx[v] + s * px + a, nb * sizeof(float), cudaMemcpyDeviceToHost, st));
-  if (h_out->converged) CK(cudaMemcpyAsync(h_out->converged + h0 + a, c->conv.p + a, nb, cudaMemcpyDeviceToHost, st));
-  if (h_out->n_evals) CK(cudaMemcpyAsync(h_out->n_evals + h0 + a, c->nev.p + a, nb * sizeof(int), cudaMemcpyDeviceToHost, st));
-  if (d_rec) {
-    CK(cudaMemcpyAsync(rec, d_rec, (size_t)capacity * reclen * sizeof(double), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(pix, d_pix, capacity * sizeof(int), cudaMemcpyDeviceToHost, st));
-    if (iters) CK(cudaMemcpyAsync(iters, d_it, 3 * capacity * sizeof(int), cudaMemcpyDeviceToHost, st));
+  phb_stats local;
+  memset(&local, 0, sizeof(local));
+  rc = phb_shard_solve(S, nullptr, 0, st, &local);
+  S->dbg_rec = nullptr; S->dbg_pix = nullptr; S->dbg_iters = nullptr; S->dbg_cap = 0;
+  if (rc) return rc;
+  CK(cudaEventRecord(evs.e[2], st));
+  rc = band_download(S, dst, flat_flags, 0, st);
+  if (rc) return rc;
+  if (rec && capacity > 0) {
+    CK(cudaMemcpyAsync(rec, c->dbg_rec.p, (size_t)capacity * reclen * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(pix, c->dbg_pix.p, capacity * sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (iters) CK(cudaMemcpyAsync(iters, c->dbg_iters.p, 3 * capacity * sizeof(int), cudaMemcpyDeviceToHost, st));
   }
-  CK(cudaEventRecord(e3, st));
+  CK(cudaEventRecord(evs.e[3], st));
   CK(cudaStreamSynchronize(st));
-  CK(cudaEventElapsedTime(&local.ms_h2d, e0, e1));
-  CK(cudaEventElapsedTime(&local.ms_d2h, e2, e3));
+  CK(cudaEventElapsedTime(&local.ms_h2d, evs.e[0], evs.e[1]));
+  CK(cudaEventElapsedTime(&local.ms_d2h, evs.e[2], evs.e[3]));
   if (stats) *stats = local;
   return PHB_OK;
 }
 
+}  // namespace
+
+extern "C" {
+
 int phb_invert_host(phb_ctx *ctx, const phb_scene_desc *desc, const float *const *h_planes, const float *h_prior,
                     int row_begin, int row_end, const phb_outputs *h_out, phb_stats *stats) {
-  return invert_host_impl(ctx, desc, h_planes, h_prior, row_begin, row_end, h_out, stats, nullptr, nullptr, nullptr, 0);
+  if (!h_planes || !h_out || !desc) return PHB_EINVAL;
+  RowSrc src; src.planes = h_planes; src.prior = h_prior; src.ncols = desc->ncols;
+  RowDst dst; dst.flat = h_out; dst.ncols = desc->ncols; dst.plane_px = (size_t)desc->nrows * desc->ncols;
+  return invert_host_one(ctx, desc, src, row_begin, row_end, dst, h_out, stats, nullptr, nullptr, nullptr, 0);
 }
 
 int phb_invert_host_debug(phb_ctx *ctx, const phb_scene_desc *desc, const float *const *h_planes, const float *h_prior,
                           int row_begin, int row_end, const phb_outputs *h_out, double *rec, int32_t *pix,
                           int32_t *n_iters, int64_t capacity, phb_stats *stats) {
-  return invert_host_impl(ctx, desc, h_planes, h_prior, row_begin, row_end, h_out, stats, rec, pix, n_iters, capacity);
+  if (!h_planes || !h_out || !desc) return PHB_EINVAL;
+  RowSrc src; src.planes = h_planes; src.prior = h_prior; src.ncols = desc->ncols;
+  RowDst dst; dst.flat = h_out; dst.ncols = desc->ncols; dst.plane_px = (size_t)desc->nrows * desc->ncols;
+  return invert_host_one(ctx, desc, src, row_begin, row_end, dst, h_out, stats, rec, pix, n_iters, capacity);
 }
 
 /* ---- one process, several GPUs: row bands over one context per device ----------------------- */
@@ -520,32 +991,36 @@ namespace {
 
 /* Relative cost of one inversion by DEPTHS-prior bin: mean evaluation count per bin (CPU oracle, Exmouth- and
  * Pilbara-shaped rasters) times the per-evaluation cost of the pixel class; the same table as
- * photic_b200/sharded.py:row_cost_from_prior (8-band balance 0.77 -> 0.89 on Pilbara). */
+ * photic_b200/sharded.py:row_cost_from_prior (8-band balance 0.77 -> 0.89 on Pilbara). Only the
+ * fallback without peer access plans by it; with peer access the devices share the work at run time. */
 const float kCostEdges[8] = {2.0f, 4.0f, 6.0f, 8.0f, 12.0f, 16.0f, 24.0f, 32.0f};
 const float kCostWeight[9] = {2.4f, 2.9f, 2.6f, 2.2f, 1.0f, 1.1f, 1.05f, 1.35f, 1.4f};
 const float kCostNoPrior = 8.0f * 2.4f; /* eight H starts, all substrates (samodel.c:2222-2241) */
 
 /* estimated work of rows [r0, r1): validity as classify_kernel decides it (samodel.c:933-947), weight by prior bin */
-void row_costs(const phb_scene_desc *d, int SB, const float *const *planes, const float *prior, int r0, int r1,
-               double *cost) {
+void row_costs(const phb_scene_desc *d, int SB, const RowSrc *src, int r0, int r1, double *cost) {
   const int nc = d->ncols;
   std::vector<unsigned char> ok(nc);
   for (int r = r0; r < r1; r++) {
-    const size_t base = (size_t)r * nc;
     for (int c = 0; c < nc; c++) ok[c] = 1;
-    for (int g = 0; g < SB; g++) {
-      const float *p = planes[g] + base;
-      for (int c = 0; c < nc; c++) {
-        const float v = p[c];
-        if (v < 0.0f || approx_equal_f(v, d->nodata, 1.0e-6f)) ok[c] = 0;
+    int g = 0;
+    for (int s = 0; s < d->n_scenes; s++)
+      for (int b = 0; b < d->n_bands[s]; b++, g++) {
+        const float *p = src->row(g, r);
+        const float nd = d->nodata_per_band ? d->nodata_band[s][b] : d->nodata;
+        for (int c = 0; c < nc; c++) {
+          const float v = p[c];
+          if (v < 0.0f || approx_equal_f(v, nd, 1.0e-6f)) ok[c] = 0;
+        }
       }
-    }
+    (void)SB;
+    const float *pr = (d->prior_present && src->has_prior()) ? src->prow(r) : nullptr;
     double acc = 0.0;
     for (int c = 0; c < nc; c++) {
       if (!ok[c]) continue;
       float w = kCostNoPrior;
-      if (d->prior_present && prior) {
-        const float e = prior[base + c];
+      if (pr) {
+        const float e = pr[c];
         if (!approx_equal_f(e, d->prior_nodata, 1.0e-6f)) {
           const float h = (e > -1.0f) ? 1.0f : fabsf(e);
           int bin = 0;
@@ -577,19 +1052,7 @@ void plan_bands(const double *cost, int nrows, int parts, int32_t *edges) {
   }
 }
 
-int scene_bands(const phb_scene_desc *d) {
-  int SB = 0;
-  for (int s = 0; s < d->n_scenes; s++) SB += d->n_bands[s];
-  return SB;
-}
-
-}  // namespace
-
-int phb_plan_row_bands(const phb_scene_desc *desc, const float *const *h_planes, const float *h_prior, int n_parts,
-                       int32_t *edges, double *row_cost) {
-  int rc = validate(desc);
-  if (rc) return rc;
-  if (!h_planes || !edges || n_parts < 1) return PHB_EINVAL;
+int plan_row_bands_src(const phb_scene_desc *desc, const RowSrc &src, int n_parts, int32_t *edges, double *row_cost) {
   const int SB = scene_bands(desc), nrows = desc->nrows;
   std::vector<double> cost(nrows, 0.0);
   int nthr = (int)std::thread::hardware_concurrency(); /* the scan is memory-bound host work: use the cores */
@@ -600,7 +1063,7 @@ int phb_plan_row_bands(const phb_scene_desc *desc, const float *const *h_planes,
   std::vector<std::thread> th;
   for (int t = 0; t < nthr; t++) {
     const int r0 = (int)((long long)nrows * t / nthr), r1 = (int)((long long)nrows * (t + 1) / nthr);
-    th.emplace_back(row_costs, desc, SB, h_planes, h_prior, r0, r1, cost.data());
+    th.emplace_back(row_costs, desc, SB, &src, r0, r1, cost.data());
   }
   for (auto &t : th) t.join();
   plan_bands(cost.data(), nrows, n_parts, edges);
@@ -608,43 +1071,123 @@ int phb_plan_row_bands(const phb_scene_desc *desc, const float *const *h_planes,
   return PHB_OK;
 }
 
-int phb_invert_host_multi(phb_ctx *const *ctxs, int n_ctx, const phb_scene_desc *desc, const float *const *h_planes,
-                          const float *h_prior, const phb_outputs *h_out, phb_stats *stats, phb_stats *per_ctx,
-                          int32_t *edges_out) {
-  if (!ctxs || n_ctx < 1 || n_ctx > 64 || !h_out) return PHB_EINVAL;
+/* every host thread arrives; nobody leaves before the last one is in */
+struct HostBarrier {
+  std::mutex m; std::condition_variable cv; int n, waiting = 0; unsigned long gen = 0;
+  explicit HostBarrier(int n_) : n(n_) {}
+  void arrive() {
+    std::unique_lock<std::mutex> lk(m);
+    const unsigned long g = gen;
+    if (++waiting == n) { waiting = 0; gen++; cv.notify_all(); }
+    else cv.wait(lk, [&] { return gen != g; });
+  }
+};
+
+/* can every device of the list read and write every other one's memory? (several contexts on one device: trivially) */
+bool all_peers(phb_ctx *const *ctxs, int n) {
+  for (int a = 0; a < n; a++)
+    for (int b = 0; b < n; b++) {
+      if (ctxs[a]->device == ctxs[b]->device) continue;
+      int can = 0;
+      if (cudaDeviceCanAccessPeer(&can, ctxs[a]->device, ctxs[b]->device) != cudaSuccess || !can) { (void)cudaGetLastError(); return false; }
+    }
+  return true;
+}
+
+int invert_host_many(phb_ctx *const *ctxs, int n_ctx, const phb_scene_desc *desc, const RowSrc &src, const RowDst &dst,
+                     const phb_outputs *flat_flags, phb_stats *stats, phb_stats *per_ctx, int32_t *edges_out) {
+  if (!ctxs || n_ctx < 1 || n_ctx > kMaxViews) return PHB_EINVAL;
   for (int k = 0; k < n_ctx; k++)
     if (!ctxs[k]) return PHB_EINVAL;
-  std::vector<int32_t> edges(n_ctx + 1);
-  int rc = phb_plan_row_bands(desc, h_planes, h_prior, n_ctx, edges.data(), nullptr);
+  int rc = validate(desc);
   if (rc) return rc;
-  const int nrows = desc->nrows, SB = scene_bands(desc);
+  const int nrows = desc->nrows;
+  std::vector<int32_t> edges(n_ctx + 1);
+  const char *e_ns = getenv("PHB_NO_STEAL");
+  const bool steal = n_ctx > 1 && !(e_ns && atoi(e_ns) != 0) && all_peers(ctxs, n_ctx);
+  if (steal || n_ctx == 1) {
+    for (int k = 0; k <= n_ctx; k++) edges[k] = (int32_t)((long long)nrows * k / n_ctx); /* equal rows: the kernels share the work */
+  } else {
+    rc = plan_row_bands_src(desc, src, n_ctx, edges.data(), nullptr);
+    if (rc) return rc;
+  }
   const int nsp = desc->n_spatial == 0 ? 1 : desc->n_spatial; /* samodel.c:2967 */
   const int halo = (nsp - 1) + (desc->n_smoothing_radius - 1);
-  const size_t full_px = (size_t)nrows * desc->ncols;
   std::vector<int> rcs(n_ctx, PHB_OK);
   std::vector<std::string> errs(n_ctx);
   std::vector<phb_stats> sts(n_ctx);
   memset(sts.data(), 0, sizeof(phb_stats) * n_ctx);
+  std::vector<phb_shard_handle> handles(n_ctx);
+  std::vector<int> active(n_ctx, 0);
+  std::vector<int64_t> own_valid(n_ctx, 0);
+  std::atomic<bool> failed(false);
+  HostBarrier bar(n_ctx);
+  auto fail = [&](int k, int code) { rcs[k] = code; if (code == PHB_ECUDA || code == PHB_ENOPEER) errs[k] = g_last_cuda_error; failed.store(true); };
   auto work = [&](int k) {
+    phb_ctx *c = ctxs[k];
     const int r0 = edges[k], r1 = edges[k + 1];
-    if (r1 <= r0) return;
     /* the band with its halo rows is a raster of its own: edge clamping then only ever happens at the real
      * edges of the scene, so band + halo == unsharded (tests: row-band shards equal the whole scene) */
     const int w0 = r0 - halo < 0 ? 0 : r0 - halo, w1 = r1 + halo > nrows ? nrows : r1 + halo;
-    phb_scene_desc dd = *desc;
-    dd.nrows = w1 - w0;
-    std::vector<const float *> pl(SB);
-    for (int g = 0; g < SB; g++) pl[g] = h_planes[g];
-    rcs[k] = invert_host_impl(ctxs[k], &dd, pl.data(), h_prior, r0 - w0, r1 - w0, h_out, &sts[k], nullptr, nullptr,
-                              nullptr, 0, HostView{w0, full_px});
-    if (rcs[k] == PHB_ECUDA) errs[k] = g_last_cuda_error;
+    phb_shard *S = nullptr;
+    cudaStream_t st = 0;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    float ms_h2d = 0.0f, ms_d2h = 0.0f;
+    if (r1 > r0) {
+      int rc2 = PHB_OK;
+      do {
+        if (cudaSetDevice(c->device) != cudaSuccess) { rc2 = PHB_ECUDA; g_last_cuda_error = "cudaSetDevice"; break; }
+        phb_scene_desc dd = *desc;
+        dd.nrows = w1 - w0;
+        dd.prior_present = (desc->prior_present && src.has_prior()) ? 1 : 0;
+        rc2 = host_band(c, &dd, r0 - w0, r1 - w0, dst.wants_stacked(), &S);
+        if (rc2) break;
+        for (int q = 0; q < 4; q++)
+          if (cudaEventCreate(&ev[q]) != cudaSuccess) { rc2 = PHB_ECUDA; g_last_cuda_error = "cudaEventCreate"; break; }
+        if (rc2) break;
+        cudaEventRecord(ev[0], st);
+        rc2 = band_upload(S, src, w0, st);
+        if (rc2) break;
+        cudaEventRecord(ev[1], st);
+        rc2 = phb_shard_prepare(S, st);
+        if (rc2) break;
+        rc2 = phb_shard_export(S, &handles[k]);
+        if (rc2) break;
+        if (cudaStreamSynchronize(st) != cudaSuccess) { rc2 = PHB_ECUDA; g_last_cuda_error = "cudaStreamSynchronize after prepare"; break; }
+        active[k] = 1;
+      } while (0);
+      if (rc2) fail(k, rc2);
+    }
+    bar.arrive(); /* every band is classified and exported */
+    if (S && active[k] && !failed.load()) {
+      std::vector<phb_shard_handle> peers;
+      if (steal)
+        for (int q = 1; q < n_ctx; q++) { const int o = (k + q) % n_ctx; if (active[o]) peers.push_back(handles[o]); }
+      int rc2 = phb_shard_solve(S, peers.data(), (int)peers.size(), st, &sts[k]);
+      if (rc2) fail(k, rc2);
+      else own_valid[k] = phb_shard_valid(S);
+    }
+    bar.arrive(); /* every device is done: results taken over NVLink have landed in their owners' planes */
+    if (S && active[k] && !failed.load()) {
+      int rc2 = PHB_OK;
+      cudaEventRecord(ev[2], st);
+      rc2 = band_download(S, dst, flat_flags, w0, st);
+      if (!rc2) {
+        cudaEventRecord(ev[3], st);
+        if (cudaStreamSynchronize(st) != cudaSuccess) { rc2 = PHB_ECUDA; g_last_cuda_error = "cudaStreamSynchronize after download"; }
+      }
+      if (!rc2) { cudaEventElapsedTime(&ms_h2d, ev[0], ev[1]); cudaEventElapsedTime(&ms_d2h, ev[2], ev[3]); }
+      sts[k].ms_h2d = ms_h2d; sts[k].ms_d2h = ms_d2h;
+      if (rc2) fail(k, rc2);
+    }
+    for (cudaEvent_t x : ev) if (x) cudaEventDestroy(x);
   };
   std::vector<std::thread> th;
   for (int k = 1; k < n_ctx; k++) th.emplace_back(work, k);
   work(0);
   for (auto &t : th) t.join();
   for (int k = 0; k < n_ctx; k++)
-    if (rcs[k]) { if (rcs[k] == PHB_ECUDA) g_last_cuda_error = errs[k]; return rcs[k]; }
+    if (rcs[k]) { if (!errs[k].empty()) g_last_cuda_error = errs[k]; return rcs[k]; }
   if (stats) {
     memset(stats, 0, sizeof(*stats));
     for (int k = 0; k < n_ctx; k++) {
@@ -661,6 +1204,35 @@ int phb_invert_host_multi(phb_ctx *const *ctxs, int n_ctx, const phb_scene_desc 
   if (per_ctx) memcpy(per_ctx, sts.data(), sizeof(phb_stats) * n_ctx);
   if (edges_out) memcpy(edges_out, edges.data(), sizeof(int32_t) * (n_ctx + 1));
   return PHB_OK;
+}
+
+}  // namespace
+
+int phb_plan_row_bands(const phb_scene_desc *desc, const float *const *h_planes, const float *h_prior, int n_parts,
+                       int32_t *edges, double *row_cost) {
+  int rc = validate(desc);
+  if (rc) return rc;
+  if (!h_planes || !edges || n_parts < 1) return PHB_EINVAL;
+  RowSrc src; src.planes = h_planes; src.prior = h_prior; src.ncols = desc->ncols;
+  return plan_row_bands_src(desc, src, n_parts, edges, row_cost);
+}
+
+int phb_invert_host_multi(phb_ctx *const *ctxs, int n_ctx, const phb_scene_desc *desc, const float *const *h_planes,
+                          const float *h_prior, const phb_outputs *h_out, phb_stats *stats, phb_stats *per_ctx,
+                          int32_t *edges_out) {
+  if (!h_planes || !h_out || !desc) return PHB_EINVAL;
+  RowSrc src; src.planes = h_planes; src.prior = h_prior; src.ncols = desc->ncols;
+  RowDst dst; dst.flat = h_out; dst.ncols = desc->ncols; dst.plane_px = (size_t)desc->nrows * desc->ncols;
+  return invert_host_many(ctxs, n_ctx, desc, src, dst, h_out, stats, per_ctx, edges_out);
+}
+
+int phb_invert_rows(phb_ctx *const *ctxs, int n_ctx, const phb_scene_desc *desc, const float *const *const *plane_rows,
+                    const float *const *prior_rows, const phb_row_outputs *out, phb_stats *stats, phb_stats *per_ctx,
+                    int32_t *edges_out) {
+  if (!plane_rows || !out || !desc) return PHB_EINVAL;
+  RowSrc src; src.plane_rows = plane_rows; src.prior_rows = prior_rows; src.ncols = desc->ncols;
+  RowDst dst; dst.rows = out; dst.ncols = desc->ncols;
+  return invert_host_many(ctxs, n_ctx, desc, src, dst, nullptr, stats, per_ctx, edges_out);
 }
 
 
@@ -767,8 +1339,12 @@ int phb_depth_sigma_host(phb_ctx *c, const phb_scene_desc *desc, const float *co
     CK(cudaMemcpyAsync(c->d_model, &M, sizeof(M), cudaMemcpyHostToDevice, st));
     SolveParams sp;
     memset(&sp, 0, sizeof(sp));
-    sp.planes = c->planes.p; sp.prior = c->prior.p;
-    sp.n_queue = c->d_scalars + 2; sp.head = c->d_scalars + 3;
+    BandView tv; /* the raster the trials read; the work items are trial chains (chain_begin), not a pixel queue */
+    memset(&tv, 0, sizeof(tv));
+    tv.planes = c->planes.p; tv.prior = c->prior.p; tv.nrows = nrows;
+    tv.n_queue[0] = c->d_scalars + 2; tv.head[0] = c->d_scalars + 3;
+    CK(cudaMemcpyAsync(c->d_views, &tv, sizeof(tv), cudaMemcpyHostToDevice, st));
+    sp.views = c->d_views; sp.n_views = 1; sp.n_classes = 1;
     sp.trial_pix = c->queue.p; sp.chain_begin = c->queue.p + n_tr;
     sp.trial_nsig = reinterpret_cast<const float *>(c->nev.p);
     sp.trial_depth = c->dbg_rec.p;

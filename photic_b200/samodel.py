@@ -253,6 +253,93 @@ class Inverter:
         return out
 
 
+class _DevView:
+    """A raw device pointer as something torch can wrap (__cuda_array_interface__, version 2)."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+class Band:
+    """A row band of a scene resident on one device and shareable with the other devices of the box (phb_shard_*,
+    include/photic_b200.h): the device-resident form of the multi-GPU path. ``desc.nrows`` counts the band's raster
+    INCLUDING its halo rows; rows [row_begin, row_end) of that raster are the band's own. The rasters live in the
+    library's allocation (one CUDA IPC handle per band); ``planes`` / ``prior`` / ``outputs`` are torch views of it."""
+
+    def __init__(self, inverter: Inverter, desc: SceneDesc, row_begin: int, row_end: int, scene_planes: bool = False):
+        import torch
+
+        self.inv, self.desc, self.row_begin, self.row_end = inverter, desc, row_begin, row_end
+        self.lib = inverter.lib
+        self.h = C.c_void_p()
+        check(self.lib.phb_shard_create(inverter.ctx, C.byref(desc), row_begin, row_end, 1 if scene_planes else 0,
+                                        C.byref(self.h)))
+        dp, dpr, o = C.c_void_p(), C.c_void_p(), Outputs()
+        check(self.lib.phb_shard_buffers(self.h, C.byref(dp), C.byref(dpr), C.byref(o)))
+        dev = torch.device("cuda", inverter.device)
+        nr, nc, ns = desc.nrows, desc.ncols, desc.n_scenes
+        sb = sum(desc.n_bands[s] for s in range(ns))
+        mb = max(desc.n_bands[s] for s in range(ns))
+
+        def view(ptr, shape, typestr="<f4"):
+            return torch.as_tensor(_DevView(ptr, shape, typestr), device=dev)
+
+        self.planes = view(dp.value, (sb, nr, nc))
+        self.prior = view(dpr.value, (nr, nc)) if dpr.value else None
+        self.outputs = {n: view(C.cast(getattr(o, n), C.c_void_p).value, (nr, nc)) for n in SCALAR_PLANES}
+        if scene_planes:
+            self.outputs["K"] = view(C.cast(o.K, C.c_void_p).value, (ns, mb, nr, nc))
+            for n in ("P", "G", "X"):
+                self.outputs[n] = view(C.cast(getattr(o, n), C.c_void_p).value, (ns, nr, nc))
+        self.outputs["converged"] = view(C.cast(o.converged, C.c_void_p).value, (nr, nc), "|u1")
+        self.outputs["n_evals"] = view(C.cast(o.n_evals, C.c_void_p).value, (nr, nc), "<i4")
+
+    def export(self) -> bytes:
+        """The band's handle (512 bytes, POD): what the other devices need to take work from this band."""
+        h = capi.ShardHandle()
+        check(self.lib.phb_shard_export(self.h, C.byref(h)))
+        return bytes(h.bytes)
+
+    @staticmethod
+    def _stream(stream, device):
+        import torch
+        s = torch.cuda.current_stream(device) if stream is None else stream
+        return C.c_void_p(s.cuda_stream)
+
+    def prepare(self, stream=None):
+        """Validity scan, output defaults and work queues of this band (asynchronous on the stream)."""
+        check(self.lib.phb_shard_prepare(self.h, self._stream(stream, self.planes.device)))
+
+    def solve(self, peers=(), stream=None):
+        """Inverts: this band's pixels first, then pixels taken from the peers' queues (handles from export(), in the
+        order to try them). Every band must be prepared before any solve starts and results are complete only once
+        every device's solve has finished -- the caller synchronises. Returns this DEVICE's stats."""
+        n = len(peers)
+        arr = (capi.ShardHandle * max(n, 1))()
+        for k, b in enumerate(peers):
+            C.memmove(C.byref(arr[k]), bytes(b), 512)
+        st = Stats()
+        check(self.lib.phb_shard_solve(self.h, arr, n, self._stream(stream, self.planes.device), C.byref(st)))
+        return st.as_dict()
+
+    def valid(self) -> int:
+        return int(self.lib.phb_shard_valid(self.h))
+
+    def close(self):
+        if self.h:
+            self.planes = self.prior = None
+            self.outputs = {}
+            self.lib.phb_shard_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 # --------------------------------------------------------------------------------------------------
 # The reference's call surface, in Python (model/samodel.h:8-19, model/common.h:69-84,194-218)
 # --------------------------------------------------------------------------------------------------
@@ -308,13 +395,19 @@ def samodel(scene_data, gridded_data, scene_indexes, nscenes, empirical_depth_pr
         inv = _default_inverter
     scs = [scene_data[scene_indexes[k]] for k in range(nscenes)]
     g0 = gridded_data[scs[0].band_indexes[0]]
-    desc = capi.make_desc(np.array([s.wavelengths for s in scs], dtype=np.int32), [s.theta_v for s in scs],
+    for s in scs:  # every grid of the call must have the shape of the first one (the reference indexes them alike)
+        for k in s.band_indexes:
+            if (gridded_data[k].nrows, gridded_data[k].ncols) != (g0.nrows, g0.ncols):
+                raise ValueError(f"grid {k} is {gridded_data[k].nrows}x{gridded_data[k].ncols}, expected {g0.nrows}x{g0.ncols}")
+    nd = [[float(gridded_data[k].nodata_value) for k in s.band_indexes] for s in scs]
+    same_nodata = all(v == nd[0][0] for row in nd for v in row)
+    desc = capi.make_desc([list(s.wavelengths)[:s.n_bands] for s in scs], [s.theta_v for s in scs],
                           [s.theta_w for s in scs], [s.H_tide for s in scs], g0.nrows, g0.ncols,
                           nodata=g0.nodata_value, prior_present=bool(empirical_depth_present),
                           prior_nodata=empirical_depths.nodata_value if empirical_depth_present else -9999.0,
                           n_smooth=n_smoothing_radius, n_spatial=n_spatial, n_bottoms=n_bottoms,
-                          r_sigma=np.array([[(s.R_sigma[b] if b < len(s.R_sigma) else 0.0) for b in range(s.n_bands)]
-                                            for s in scs]))
+                          r_sigma=[[(s.R_sigma[b] if b < len(s.R_sigma) else 0.0) for b in range(s.n_bands)] for s in scs],
+                          nodata_band=None if same_nodata else nd)
     planes = [gridded_data[k].array for s in scs for k in s.band_indexes]
     buffers = {"depth": depth, "model_error": model_error, "bottom_albedo": bottom_albedo, "bottom_sand": bottom_sand,
                "bottom_seagrass": bottom_seagrass, "bottom_coral": bottom_coral, "K_min": K_min,

@@ -7,14 +7,77 @@ inverting; the only exchanges are
   * the halo rows between neighbouring bands when every rank holds just its own rows
     (point-to-point NCCL send/recv over NVLink), and
   * the final gather of the output planes to rank 0.
-Bands are contiguous and balanced by estimated cost, not by row count: a shallow-water pixel
-(all NBOTTOMS substrates, n = 81..87) costs ~3x a deep one (sand only, n = 45..51).
+Load balance (round 2): the bands are EQUAL row counts and the devices share the work at run time. Every rank's band
+lives in a library allocation that the other ranks map (CUDA IPC over NVLink peer access, `BandGroup` below); a solve
+kernel that runs out of its own pixels takes pixels from its neighbours' queues, reads their neighbourhoods from the
+owner's planes and stores the results into the owner's planes -- pixel by pixel, no collective and no cost model on the
+data path. The cost-balanced contiguous plan (`plan_row_bands`, `row_cost_from_prior`: a shallow-water pixel with all
+NBOTTOMS substrates costs ~3x a sand-only one) remains for boxes without peer access.
 """
 from __future__ import annotations
 
 import numpy as np
 import torch
 import torch.distributed as dist
+
+
+class BandGroup:
+    """This rank's Band (photic_b200.samodel.Band) plus the handles of every other rank's band, exchanged once.
+    step() = prepare -> [all ranks prepared] -> solve with work sharing -> [all ranks done]; the two synchronisation
+    points are stream-ordered one-element all-reduces under NCCL (no host round trip) and barriers under gloo."""
+
+    def __init__(self, inverter, desc, row_begin: int, row_end: int, rank: int, world: int, group=None,
+                 scene_planes: bool = False, share: bool = True):
+        from .samodel import Band
+        self.rank, self.world, self.group = rank, world, group
+        self.band = Band(inverter, desc, row_begin, row_end, scene_planes)
+        self.peers: list[bytes] = []
+        self.shared = False
+        dev = self.band.planes.device
+        self._nccl = world > 1 and dist.get_backend(group) == "nccl"
+        self._flag = torch.zeros(1, device=dev)
+        if world > 1 and share:
+            mine = torch.frombuffer(bytearray(self.band.export()), dtype=torch.uint8)
+            if self._nccl:
+                mine = mine.to(dev)
+            parts = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(parts, mine, group=group)
+            hs = [bytes(p.cpu().numpy().tobytes()) for p in parts]
+            self.peers = [hs[(rank + q) % world] for q in range(1, world)]  # take work from the next rank first
+            self.shared = True
+
+    def sync(self):
+        if self.world == 1:
+            return
+        if self._nccl:  # stream-ordered: the kernels queued after it start once every rank has reached it
+            dist.all_reduce(self._flag, group=self.group)
+        else:
+            torch.cuda.synchronize(self._flag.device)
+            dist.barrier(group=self.group)
+
+    def step(self, stream=None) -> dict:
+        """Inverts the band (its rasters must have been written into band.planes / band.prior). Returns this
+        DEVICE's stats: with work sharing `n_valid` counts the pixels it inverted, its own or its neighbours'."""
+        from . import capi
+        self.band.prepare(stream)
+        self.sync()
+        try:
+            st = self.band.solve(self.peers, stream)
+        except capi.PhoticError as e:  # no peer access on this box: every rank works on its own band only
+            if getattr(e, "code", None) != capi.PHB_ENOPEER:
+                raise
+            self.peers, self.shared = [], False
+            st = self.band.solve([], stream)
+        self.sync()
+        st["shared"] = self.shared
+        return st
+
+    def close(self):
+        self.band.close()
+
+
+def equal_row_bands(nrows: int, world: int) -> list[tuple[int, int]]:
+    return [(nrows * k // world, nrows * (k + 1) // world) for k in range(world)]
 
 
 def halo_rows(n_spatial: int, n_smoothing_radius: int) -> int:

@@ -134,7 +134,7 @@ void kat_objective_body() {
   __syncthreads();
   Warp w;
   const int lane = threadIdx.x & 31, SB = p.L.SB, Ns = p.L.Ns;
-  bind_warp(w, p, phb_smem, 0, 0);
+  bind_warp(w, p, p.L, phb_smem, 0, 0);
   Pixel px;
   px.Nr = g_kat.n_regions; px.Nb = g_kat.nb_active; px.origin = g_kat.origin;
   size_pixel(px, lane, SB, Ns, p.L.simplex_doubles, 0);
@@ -156,6 +156,53 @@ void kat_objective_body() {
     __syncwarp();
   }
 }
+
+/* wires one band (view 0) and its work queues into sp the way the host library does (photic_b200.cu: bind_queues):
+ * NBOTTOMS = 3 -> two pixel classes, queue[0] = pixels with all substrates, queue[1] = sand-only pixels (h_prior > 8 m) */
+struct EmuBand {
+  phb::BandView view;
+  std::vector<int> q0, q1;
+  int scal[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  bool two = false;
+  void wire(const phb::ModelConst &M, const float *planes, const float *prior, const int *queue, int n_queue,
+            const phb_outputs &out) {
+    using namespace phb;
+    memset(&view, 0, sizeof(view));
+    view.planes = planes; view.prior = M.prior_present ? prior : nullptr; view.nrows = M.nrows; view.out = out;
+    two = M.n_bottoms == 3 && getenv("PHB_ONE_CLASS") == nullptr;
+    q0.clear(); q1.clear();
+    for (int k = 0; k < n_queue; k++) {
+      bool deep = false;
+      if (two && view.prior != nullptr) {
+        const float e = view.prior[queue[k]];
+        if (!approx_equal_f(e, M.prior_nodata, 1.0e-6f)) deep = ((e > -1.0) ? 1.0 : fabs((double)e)) > 8.0;
+      }
+      (deep ? q1 : q0).push_back(queue[k]);
+    }
+    q0.push_back(0); q1.push_back(0); /* never empty vectors */
+    scal[0] = (int)q0.size() - 1; scal[1] = (int)q1.size() - 1; scal[2] = n_queue;
+    view.queue[0] = q0.data(); view.n_queue[0] = &scal[0]; view.head[0] = &scal[3];
+    view.queue[1] = q1.data(); view.n_queue[1] = &scal[1]; view.head[1] = &scal[4];
+  }
+  void bind(phb::SolveParams &sp, const phb::ModelConst &M, int NrMax, int simplex_smem_bytes) {
+    using namespace phb;
+    sp.views = &view; sp.n_views = 1; sp.n_classes = two ? 2 : 1;
+    if (two) { /* as launch_solve: same CTA block and warp stride, the left-over of the warp block holds simplex rows */
+      sp.L1 = make_layout(M.SB, M.n_scenes, 1, NrMax);
+      sp.L1.cta_bytes = sp.L.cta_bytes;
+      long long cache1 = (long long)sp.L.warp_bytes - sp.L1.w_simplex;
+      const long long simplex1 = (long long)(sp.L1.nmax + 1) * sp.L1.nmax * 8;
+      if (cache1 > simplex1) cache1 = simplex1;
+      if (cache1 > simplex_smem_bytes) cache1 = simplex_smem_bytes;
+      if (cache1 < 0) cache1 = 0;
+      add_simplex_cache(sp.L1, (int)cache1);
+      sp.L1.warp_bytes = sp.L.warp_bytes;
+      sp.L1.tmem_cols = 0;
+    } else {
+      sp.L1 = sp.L;
+    }
+  }
+};
 
 const uint64_t kExpTab[2 * PHM_N] = PHM_EXP_TAB;
 const double kLogTab[2 * PHM_N] = PHM_LOG_TAB;
@@ -200,25 +247,27 @@ int emu_invert(const void *model, int64_t model_size, const float *planes, const
   if ((size_t)sp.L.cta_bytes + (size_t)sp.L.warp_bytes > sizeof(phb_smem)) return 2;
   memset(phb_smem, 0xcd, sizeof(phb_smem)); /* uninitialised shared memory is not zero on the device either */
   std::vector<double> slab(slab_doubles, 0.0);
-  int n_q = n_queue, head = 0;
   unsigned long long cnt[4] = {0, 0, 0, 0};
   double fl = 0.0;
   const size_t px = (size_t)M.nrows * M.ncols;
   sp.M = &M;
-  sp.planes = planes; sp.prior = M.prior_present ? prior : nullptr;
-  sp.queue = queue; sp.n_queue = &n_q; sp.head = &head;
   sp.slabs = slab.data(); sp.slab_stride = slab_doubles;
+  phb_outputs o;
+  memset(&o, 0, sizeof(o));
   if (out9) {
-    sp.out.depth = out9; sp.out.model_error = out9 + px; sp.out.bottom_albedo = out9 + 2 * px;
-    sp.out.bottom_sand = out9 + 3 * px; sp.out.bottom_seagrass = out9 + 4 * px; sp.out.bottom_coral = out9 + 5 * px;
-    sp.out.K_min = out9 + 6 * px; sp.out.bottom_type = out9 + 7 * px; sp.out.index_optical_depth = out9 + 8 * px;
+    o.depth = out9; o.model_error = out9 + px; o.bottom_albedo = out9 + 2 * px;
+    o.bottom_sand = out9 + 3 * px; o.bottom_seagrass = out9 + 4 * px; o.bottom_coral = out9 + 5 * px;
+    o.K_min = out9 + 6 * px; o.bottom_type = out9 + 7 * px; o.index_optical_depth = out9 + 8 * px;
   }
-  sp.out.converged = converged; sp.out.n_evals = n_evals;
+  o.converged = converged; o.n_evals = n_evals;
+  EmuBand band;
+  band.wire(M, planes, prior, queue, n_queue, o);
+  band.bind(sp, M, NrMax, simplex_smem_bytes);
   sp.dbg_rec = rec; sp.dbg_pix = pix; sp.dbg_iters = iters; sp.reclen = emu_record_len(model); sp.dbg_capacity = n_queue;
   sp.counters = cnt; sp.flops = &fl;
   sp.exp_tab = reinterpret_cast<const unsigned long long *>(kExpTab); sp.log_tab = kLogTab; sp.pow_tab = kPowTab;
-  if (sp.L.SBP == 32) g_kernel = M.n_bottoms == 3 ? solve_kernel<3, 32, false> : solve_kernel<0, 32, false>;
-  else g_kernel = M.n_bottoms == 3 ? solve_kernel<3, kMaxSB, false> : solve_kernel<0, kMaxSB, false>;
+  if (sp.L.SBP == 32) g_kernel = band.two ? solve_kernel<3, 32, false> : solve_kernel<0, 32, false>;
+  else g_kernel = band.two ? solve_kernel<3, kMaxSB, false> : solve_kernel<0, kMaxSB, false>;
   g_params = &sp;
   g_body = body_solve;
   run_warp();
@@ -275,18 +324,27 @@ int emu_invert_raster(const void *model, int64_t model_size, const float *planes
   if ((size_t)sp.L.cta_bytes + (size_t)sp.L.warp_bytes > sizeof(phb_smem)) return 2;
   memset(phb_smem, 0xcd, sizeof(phb_smem));
   std::vector<double> slab(slab_doubles, 0.0);
-  int head = 0;
   unsigned long long cnt[4] = {0, 0, 0, 0};
   double fl = 0.0;
-  sp.M = &M; sp.planes = planes; sp.prior = cp.prior;
-  sp.queue = queue.data(); sp.n_queue = &scal[2]; sp.head = &head;
+  sp.M = &M;
   sp.slabs = slab.data(); sp.slab_stride = slab_doubles;
-  sp.out = o;
+  EmuBand band; /* the device's two lists as classify_kernel left them (their concatenation for the generic kernel) */
+  memset(&band.view, 0, sizeof(band.view));
+  band.view.planes = planes; band.view.prior = cp.prior; band.view.nrows = M.nrows; band.view.out = o;
+  band.two = M.n_bottoms == 3 && getenv("PHB_ONE_CLASS") == nullptr;
+  if (band.two) {
+    band.view.queue[0] = q_shallow.data(); band.view.n_queue[0] = &scal[0]; band.view.head[0] = &band.scal[3];
+    band.view.queue[1] = q_deep.data(); band.view.n_queue[1] = &scal[1]; band.view.head[1] = &band.scal[4];
+  } else {
+    band.view.queue[0] = queue.data(); band.view.n_queue[0] = &scal[2]; band.view.head[0] = &band.scal[3];
+    band.view.queue[1] = queue.data(); band.view.n_queue[1] = &band.scal[5]; band.view.head[1] = &band.scal[4];
+  }
+  band.bind(sp, M, (2 * nsp - 1) * (2 * nsp - 1), simplex_smem_bytes);
   sp.dbg_rec = rec; sp.dbg_pix = pix; sp.dbg_iters = iters; sp.reclen = emu_record_len(model); sp.dbg_capacity = (long long)win;
   sp.counters = cnt; sp.flops = &fl;
   sp.exp_tab = reinterpret_cast<const unsigned long long *>(kExpTab); sp.log_tab = kLogTab; sp.pow_tab = kPowTab;
-  if (sp.L.SBP == 32) g_kernel = M.n_bottoms == 3 ? solve_kernel<3, 32, false> : solve_kernel<0, 32, false>;
-  else g_kernel = M.n_bottoms == 3 ? solve_kernel<3, kMaxSB, false> : solve_kernel<0, kMaxSB, false>;
+  if (sp.L.SBP == 32) g_kernel = band.two ? solve_kernel<3, 32, false> : solve_kernel<0, 32, false>;
+  else g_kernel = band.two ? solve_kernel<3, kMaxSB, false> : solve_kernel<0, kMaxSB, false>;
   g_params = &sp;
   g_body = body_solve;
   run_warp();

@@ -59,7 +59,12 @@ class Emulator:
                                  int(simplex_smem_bytes), vp(rec), vp(pix), vp(it), vp(out9), vp(conv), vp(nev), vp(cnt),
                                  C.byref(fl))
         assert rc == 0, rc
-        assert np.array_equal(pix, q)
+        # records come back in queue order: the pixels of class 0 (all substrates) first, then the sand-only ones
+        a, b = np.argsort(pix, kind="stable"), np.argsort(q, kind="stable")
+        assert np.array_equal(pix[a], q[b])
+        back = np.empty(nq, dtype=np.int64)
+        back[b] = a
+        rec, it = rec[back], it[back]
         return {"rec": rec, "n_evals": it[:, 0], "converged": it[:, 1] & 1, "n_iters": it[:, 1] >> 1, "n_restarts": it[:, 2],
                 "planes": out9,
                 "converged_plane": conv, "n_evals_plane": nev, "counters": cnt, "alg_flops": fl.value}

@@ -16,7 +16,7 @@ def test_reference_arm_prints_one_json_line(oracle_port):
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "pixel inversions/s" and d["unit"] == "px/s"
-    assert d["higher_is_better"] is True and d["scaling"] == "weak" and d["dtype"] == "f64" and d["data"] == "synthetic"
+    assert d["higher_is_better"] is True and d["scaling"] == "strong" and d["dtype"] == "f64" and d["data"] == "synthetic"
     assert d["value"] > 0 and d["steps"] == 1 and d["n_gpus"] == 1 and "workload" in d["config"]
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]

@@ -181,3 +181,45 @@ def test_emulated_kernel_on_mined_reference_pixels(emu, name, take):
         assert got["converged"].tolist() == [0, 0, 1] and (got["n_evals"] > 5000).all()
     else:
         assert (got["n_restarts"] == 1).all()
+
+
+def test_emulated_kernel_tests_every_grid_against_its_own_nodata(emu, oracle_port):
+    """Per-grid nodata values (phb_scene_desc.nodata_band; samodel.c:683, 941, 2999-3003): the nodata cells of three grids
+    re-coded to 0, -1 and 12345 and declared per grid give the records of the uniformly coded scene."""
+    from oracle.binding import SceneCfg
+    from photic_b200 import capi, scene
+    spec, pl, pr, pi, pj, capi, scene, SceneCfg = _case("murion", 10, 8, {}, 6)
+    ref = oracle_port.invert_pixels(SceneCfg.from_spec(spec), pl, scene.NODATA, pr, scene.NODATA, pi, pj)
+    pl2 = pl.copy()
+    nd = [[float(scene.NODATA)] * 4 for _ in range(spec.n_dates)]
+    for (s, b), v in {(0, 1): 0.0, (1, 3): -1.0, (3, 0): 12345.0}.items():
+        g = 4 * s + b
+        assert (pl2[g] == scene.NODATA).any() and not (pl2[g] == v).any()
+        pl2[g][pl2[g] == scene.NODATA] = v
+        nd[s][b] = v
+    desc = capi.make_desc(spec.wavelengths, spec.theta_view, [spec.theta_sun(s) for s in range(spec.n_dates)],
+                          [spec.h_tide(s) for s in range(spec.n_dates)], spec.nrows, spec.ncols, nodata_band=nd,
+                          r_sigma=spec.r_sigma)
+    got = emu.invert_pixels(desc, pl2, pr, pi, pj)
+    assert np.array_equal(got["n_evals"], ref["n_evals"]) and bits_equal(got["rec"], ref["rec"]).all()
+    assert (ref["rec"][:, 13] < 9).any()  # some of the pixels do lose neighbours to nodata
+
+
+def test_emulated_generic_kernel_on_the_default_substrate_count(oracle_port, monkeypatch):
+    """PHB_ONE_CLASS=1: NBOTTOMS = 3 through the run-time-substrate-count kernel and ONE queue (the path every other
+    NBOTTOMS takes) instead of the two compile-time pixel classes; same bits."""
+    monkeypatch.setenv("PHB_ONE_CLASS", "1")
+    _check(Emulator(), oracle_port, "exmouth", 12, 10, {}, 4, 6000)
+
+
+def test_ragged_band_lists_reach_the_model_constants(product_lib):
+    """Scenes with different band counts (mixed sensors, samodel.c:403-409) through make_desc -> phb_band_tables."""
+    from photic_b200 import capi
+    d = capi.make_desc([[443, 482, 561, 655], [443, 561, 655], [482, 561]], 0.0, [25.0, 28.0, 31.0], [0.0, 0.1, 0.2], 4, 5,
+                       r_sigma=[[1e-4] * 4, [2e-4] * 3, [3e-4] * 2])
+    assert [d.n_bands[s] for s in range(3)] == [4, 3, 2] and d.r_sigma[2][1] == 3e-4 and d.wavelengths[1][2] == 655
+    tab = np.zeros((3, capi.MAX_BANDS, 4 + capi.MAX_BOTTOMS))
+    aux = np.zeros(1 + 2 * 3)
+    capi.check(product_lib.phb_band_tables(d, tab.ctypes.data_as(capi._dp), aux.ctypes.data_as(capi._dp)))
+    assert np.array_equal(tab[0, 0], tab[1, 0]) and np.array_equal(tab[0, 2], tab[1, 1]) and np.array_equal(tab[0, 1], tab[2, 0])
+    assert (tab[1, 3] == 0).all() and (tab[2, 2:] == 0).all() and (tab[2, :2, :4] > 0).all()
