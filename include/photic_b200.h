@@ -214,7 +214,7 @@ void phb_shard_destroy(phb_shard *s);
  *   chain_mode  PHB_SIGMA_CHAIN_REFERENCE: one hot-start chain through all trials, as the reference runs them
  *               (inherently serial: one warp works, ~10 ms per trial);
  *               PHB_SIGMA_CHAIN_PER_INTERVAL: the chain restarts cold at every depth interval, intervals run
- *               in parallel (the default of the samodel() shim; equals the reference modified the same way)
+ *               in parallel (the shim's PHOTIC_B200_SIGMA_CHAIN=interval; equals the reference modified the same way)
  *   h_depth_sigma [nrows][ncols] out; table (nullable) [PHB_SIGMA_MAX_INTERVALS] out; trials (nullable)
  *               [PHB_SIGMA_MAX_INTERVALS][n_samples] out: the trial depths (0 = no pixel found / no prior)
  * A DEPTHS prior is required (PHB_EINVAL otherwise): without one the reference starts a hot trial from
@@ -226,6 +226,13 @@ void phb_shard_destroy(phb_shard *s);
 int phb_depth_sigma_host(phb_ctx *ctx, const phb_scene_desc *desc, const float *const *h_planes, const float *h_prior,
                          const float *h_depth, unsigned seed, int n_samples, int chain_mode, int max_intervals,
                          float *h_depth_sigma, double *table, int32_t *n_intervals, double *trials, phb_stats *stats);
+
+/* The same for rasters held as row pointers (geogrid.array): what the samodel() shim calls. Called directly after
+ * phb_invert_rows() on one device with the same plane_rows array it reuses the rasters that call left on the device. */
+int phb_depth_sigma_rows(phb_ctx *ctx, const phb_scene_desc *desc, const float *const *const *plane_rows,
+                         const float *const *prior_rows, const float *const *depth_rows, unsigned seed, int n_samples,
+                         int chain_mode, int max_intervals, float *const *sigma_rows, double *table, int32_t *n_intervals,
+                         double *trials, phb_stats *stats);
 
 /* Parity-test hook: like phb_invert_host but also returns the full-precision per-pixel record
  * (layout of oracle/ref_harness.c: 16 + n_scenes*max_bands + 3*n_scenes doubles) for every

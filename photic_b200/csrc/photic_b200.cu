@@ -196,6 +196,7 @@ struct phb_shard {
   struct Mapped { long long pid; unsigned long long base; unsigned char *ptr; bool ipc; };
   std::vector<Mapped> mapped;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  const void *resident_src = nullptr; /* the host rasters whose rows the band currently holds (host entry points) */
   /* debug records of the next solve (parity tests; own band only) */
   double *dbg_rec = nullptr; int *dbg_pix = nullptr, *dbg_iters = nullptr; long long dbg_cap = 0;
 };
@@ -931,8 +932,10 @@ int invert_host_one(phb_ctx *c, const phb_scene_desc *desc, const RowSrc &src, i
   } evs;
   for (int k = 0; k < 4; k++) CK(cudaEventCreate(&evs.e[k]));
   CK(cudaEventRecord(evs.e[0], st));
+  S->resident_src = nullptr;
   rc = band_upload(S, src, 0, st);
   if (rc) return rc;
+  if (row_begin == 0 && row_end == desc->nrows && src.plane_rows) S->resident_src = (const void *)src.plane_rows;
   CK(cudaEventRecord(evs.e[1], st));
   const int reclen = phb_debug_record_len(desc);
   S->dbg_rec = nullptr; S->dbg_pix = nullptr; S->dbg_iters = nullptr; S->dbg_cap = 0;
@@ -1254,13 +1257,17 @@ float rand_signed(float max) {                                     /* frand2, co
 }
 }  // namespace
 
-int phb_depth_sigma_host(phb_ctx *c, const phb_scene_desc *desc, const float *const *h_planes, const float *h_prior,
-                         const float *h_depth, unsigned seed, int n_samples, int chain_mode, int max_intervals,
-                         float *h_depth_sigma, double *table, int32_t *n_intervals, double *trials, phb_stats *stats) {
-  if (!c || !h_planes || !h_depth || !h_depth_sigma) return PHB_EINVAL;
+}  /* extern "C" */
+
+/* rasters by row (RowSrc), the depth plane and the sigma plane by row accessors: serves both host layouts */
+template <class DepthRow, class SigmaRow>
+static int depth_sigma_impl(phb_ctx *c, const phb_scene_desc *desc, const RowSrc &src, bool may_reuse, DepthRow depth_row,
+                            SigmaRow sigma_row, unsigned seed, int n_samples, int chain_mode, int max_intervals, double *table,
+                            int32_t *n_intervals, double *trials, phb_stats *stats) {
+  if (!c) return PHB_EINVAL;
   int rc = validate(desc);
   if (rc) return rc;
-  if (!desc->prior_present || !h_prior) return PHB_EINVAL; /* see the header: hot trials need the DEPTHS prior */
+  if (!desc->prior_present || !src.has_prior()) return PHB_EINVAL; /* see the header: hot trials need the DEPTHS prior */
   if (n_samples < 1 || n_samples > 4096) return PHB_EINVAL;
   if (max_intervals < 1 || max_intervals > PHB_SIGMA_MAX_INTERVALS) max_intervals = PHB_SIGMA_MAX_INTERVALS;
   if (chain_mode != PHB_SIGMA_CHAIN_REFERENCE && chain_mode != PHB_SIGMA_CHAIN_PER_INTERVAL) return PHB_EINVAL;
@@ -1273,9 +1280,12 @@ int phb_depth_sigma_host(phb_ctx *c, const phb_scene_desc *desc, const float *co
   /* interval table bounds, samodel.c:1381-1387 (depth here is the negated plane: -h_depth is the reference's) */
   const int n_trials = (int)sqrt((double)(nrows * ncols));
   float mx = -1.0e10f; /* array_max2(depth, ., ., 0.0), common.c:1240-1258 */
-  for (size_t q = 0; q < px; q++) {
-    const float dq = -h_depth[q];
-    if (!approx_equal_f(dq, 0.0f, 1.0e-4f) && dq > mx) mx = dq;
+  for (int r = 0; r < nrows; r++) {
+    const float *dr = depth_row(r);
+    for (int q = 0; q < ncols; q++) {
+      const float dq = -dr[q];
+      if (!approx_equal_f(dq, 0.0f, 1.0e-4f) && dq > mx) mx = dq;
+    }
   }
   double maxd = mx;
   if (!(maxd > 0.0)) maxd = 0.0; /* nothing inverted: no interval (the reference would index with (int)-1e10) */
@@ -1298,12 +1308,12 @@ int phb_depth_sigma_host(phb_ctx *c, const phb_scene_desc *desc, const float *co
       for (int kt = 0; kt < n_trials; kt++) {
         i = rand_below(0, nrows);
         j = rand_below(0, ncols);
-        const float dq = -h_depth[(size_t)i * ncols + j];
+        const float dq = -depth_row(i)[j];
         if (dq > d && dq < d + 0.25) { found = true; break; }
       }
       if (!found) continue;                          /* trial_depths[k_sample] = 0 */
       const float ns = (float)(double)rand_signed(1.0); /* drawn before the prior test, samodel.c:1425 */
-      if (approx_equal_f(h_prior[(size_t)i * ncols + j], desc->prior_nodata, 1.0e-6f)) continue;
+      if (approx_equal_f(src.prow(i)[j], desc->prior_nodata, 1.0e-6f)) continue;
       t_pix.push_back(i * ncols + j);
       t_nsig.push_back(ns);
       t_slot.push_back(kd * n_samples + ks);
@@ -1317,11 +1327,31 @@ int phb_depth_sigma_host(phb_ctx *c, const phb_scene_desc *desc, const float *co
   memset(&local, 0, sizeof(local));
   if (n_tr > 0) {
     cudaStream_t st = 0;
-    CK(c->planes.ensure(px * SB));
-    for (int g = 0; g < SB; g++)
-      CK(cudaMemcpyAsync(c->planes.p + g * px, h_planes[g], px * sizeof(float), cudaMemcpyHostToDevice, st));
-    CK(c->prior.ensure(px));
-    CK(cudaMemcpyAsync(c->prior.p, h_prior, px * sizeof(float), cudaMemcpyHostToDevice, st));
+    /* the rasters on the device: those the inversion of this very raster left in the context's band, else a fresh copy */
+    const float *d_planes = nullptr, *d_prior = nullptr;
+    {
+      phb_scene_desc dd = *desc;
+      dd.prior_present = 1;
+      phb_shard *S = c->host_shard;
+      if (may_reuse && S && S->resident_src != nullptr && memcmp(&S->desc, &dd, sizeof(dd)) == 0 && S->view.prior &&
+          S->resident_src == (const void *)src.plane_rows) {
+        d_planes = S->view.planes; d_prior = S->view.prior;
+        S->resident_src = nullptr; /* good for the call that directly follows the inversion only */
+      } else {
+        CK(c->planes.ensure(px * SB));
+        CK(c->prior.ensure(px));
+        rc = ring_open(c);
+        if (rc) return rc;
+        int slot = 0;
+        for (int g = 0; g < SB; g++) {
+          rc = ring_upload(c, slot, [&](long long r) { return src.row(g, r); }, 0, nrows, ncols, c->planes.p + g * px, st);
+          if (rc) return rc;
+        }
+        rc = ring_upload(c, slot, [&](long long r) { return src.prow(r); }, 0, nrows, ncols, c->prior.p, st);
+        if (rc) return rc;
+        d_planes = c->planes.p; d_prior = c->prior.p;
+      }
+    }
     /* trial arrays: pix | chain_begin as ints, n_sigma as floats, depths as doubles */
     CK(c->queue.ensure((size_t)n_tr + n_chains + 1));
     CK(c->nev.ensure(n_tr));
@@ -1341,7 +1371,7 @@ int phb_depth_sigma_host(phb_ctx *c, const phb_scene_desc *desc, const float *co
     memset(&sp, 0, sizeof(sp));
     BandView tv; /* the raster the trials read; the work items are trial chains (chain_begin), not a pixel queue */
     memset(&tv, 0, sizeof(tv));
-    tv.planes = c->planes.p; tv.prior = c->prior.p; tv.nrows = nrows;
+    tv.planes = d_planes; tv.prior = d_prior; tv.nrows = nrows;
     tv.n_queue[0] = c->d_scalars + 2; tv.head[0] = c->d_scalars + 3;
     CK(cudaMemcpyAsync(c->d_views, &tv, sizeof(tv), cudaMemcpyHostToDevice, st));
     sp.views = c->d_views; sp.n_views = 1; sp.n_classes = 1;
@@ -1384,21 +1414,48 @@ int phb_depth_sigma_host(phb_ctx *c, const phb_scene_desc *desc, const float *co
     tab[k] = cnt == 0 ? 0.0 : sqrt(sumdev / ((double)cnt));
   }
   /* every cell gets the sigma of its interval (d, d + 0.25], samodel.c:1463-1477 */
-  for (size_t q = 0; q < px; q++) {
-    const float dq = -h_depth[q];
-    float sg = 0.0f;
-    if (dq > 0.0) {
-      int k = 0;
-      for (double d = 0.0; d < maxd; d += 0.25, k++)
-        if (dq > d && dq <= d + 0.25) { sg = (float)tab[k]; break; }
+  for (int r = 0; r < nrows; r++) {
+    const float *dr = depth_row(r);
+    float *sr = sigma_row(r);
+    for (int q = 0; q < ncols; q++) {
+      const float dq = -dr[q];
+      float sg = 0.0f;
+      if (dq > 0.0) {
+        int k = 0;
+        for (double d = 0.0; d < maxd; d += 0.25, k++)
+          if (dq > d && dq <= d + 0.25) { sg = (float)tab[k]; break; }
+      }
+      sr[q] = sg;
     }
-    h_depth_sigma[q] = sg;
   }
   if (table) for (int k = 0; k < n_int; k++) table[k] = tab[k];
   if (n_intervals) *n_intervals = n_int;
   if (trials) memcpy(trials, td.data(), (size_t)n_int * n_samples * sizeof(double));
   if (stats) *stats = local;
   return PHB_OK;
+}
+
+extern "C" {
+
+int phb_depth_sigma_host(phb_ctx *c, const phb_scene_desc *desc, const float *const *h_planes, const float *h_prior,
+                         const float *h_depth, unsigned seed, int n_samples, int chain_mode, int max_intervals,
+                         float *h_depth_sigma, double *table, int32_t *n_intervals, double *trials, phb_stats *stats) {
+  if (!c || !desc || !h_planes || !h_depth || !h_depth_sigma) return PHB_EINVAL;
+  RowSrc src; src.planes = h_planes; src.prior = h_prior; src.ncols = desc->ncols;
+  const int nc = desc->ncols;
+  return depth_sigma_impl(c, desc, src, false, [=](int r) { return h_depth + (size_t)r * nc; },
+                          [=](int r) { return h_depth_sigma + (size_t)r * nc; }, seed, n_samples, chain_mode, max_intervals,
+                          table, n_intervals, trials, stats);
+}
+
+int phb_depth_sigma_rows(phb_ctx *c, const phb_scene_desc *desc, const float *const *const *plane_rows,
+                         const float *const *prior_rows, const float *const *depth_rows, unsigned seed, int n_samples,
+                         int chain_mode, int max_intervals, float *const *sigma_rows, double *table, int32_t *n_intervals,
+                         double *trials, phb_stats *stats) {
+  if (!c || !desc || !plane_rows || !depth_rows || !sigma_rows) return PHB_EINVAL;
+  RowSrc src; src.plane_rows = plane_rows; src.prior_rows = prior_rows; src.ncols = desc->ncols;
+  return depth_sigma_impl(c, desc, src, true, [=](int r) { return depth_rows[r]; }, [=](int r) { return sigma_rows[r]; }, seed,
+                          n_samples, chain_mode, max_intervals, table, n_intervals, trials, stats);
 }
 
 /* ---- known-answer hooks ----------------------------------------------------------------------- */

@@ -71,6 +71,14 @@ def test_shim_exports_reference_symbol(product_lib):
     assert hasattr(lib, "samodel")
 
 
+def _build_mini_model(tmp_path, so, extra=()):
+    exe = str(tmp_path / "mini_model")
+    subprocess.run(["gcc", "-O1", "-Wall", *extra, "-I", os.path.join(ROOT, "photic_b200", "host"),
+                    os.path.join(ROOT, "tests", "csrc", "mini_model.c"), "-o", exe, "-L", os.path.dirname(so),
+                    "-lsamodel_b200", "-Wl,-rpath," + os.path.dirname(so)], check=True)
+    return exe
+
+
 def test_c_program_linking_the_drop_in_fails_loudly_without_a_device(product_lib, tmp_path):
     """A C caller built like the reference's REPL (tests/csrc/mini_model.c) linked against the drop-in: on a machine
     without a CUDA device samodel() must print the error and exit(1) -- the reference's own failure convention
@@ -80,15 +88,40 @@ def test_c_program_linking_the_drop_in_fails_loudly_without_a_device(product_lib
         pytest.skip("a CUDA device is present: the no-device path cannot be observed")
     from photic_b200 import build
     so = build.build_host_shim()
-    exe = str(tmp_path / "mini_model")
-    subprocess.run(["gcc", "-O1", "-Wall", "-I", os.path.join(ROOT, "photic_b200", "host"),
-                    os.path.join(ROOT, "tests", "csrc", "mini_model.c"), "-o", exe, "-L", os.path.dirname(so),
-                    "-lsamodel_b200", "-Wl,-rpath," + os.path.dirname(so)], check=True)
+    exe = _build_mini_model(tmp_path, so)
     for env_extra in ({}, {"PHOTIC_B200_DEVICES": "all"}, {"PHOTIC_B200_DEVICES": "0,1"}):
         r = subprocess.run([exe], capture_output=True, text=True, env={**os.environ, **env_extra}, timeout=120)
         assert r.returncode == 1, (env_extra, r.returncode, r.stdout[-400:], r.stderr[-400:])
         assert "ERROR: photic_b200" in r.stdout and "no CPU fallback" in r.stdout
         assert "mini_model: depth" not in r.stdout
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference sources absent")
+def test_shim_builds_and_links_inside_the_reference_tree(product_lib, tmp_path):
+    """INTEGRATION.md section 1, executed: the shim compiled INSTEAD of samodel.c with -DPHOTIC_REFERENCE_TREE against the
+    reference's own headers (its `scene`, `geogrid`, `bool`, MAX_STRING_LEN, trim()), linked with the reference's
+    common.c and a caller that uses the reference's types, and libphotic_b200. netcdf.h / cpgplot.h are the two empty
+    stand-in headers the oracle build uses (the libraries are not in this image). Without a CUDA device the program
+    must stop the reference's way: message + exit(1)."""
+    import torch
+    from photic_b200 import build
+    lib = build.build()
+    exe = str(tmp_path / "mini_ref")
+    inc = ["-I", os.path.join(ROOT, "oracle", "ref_shim"), "-I", REF, "-I", os.path.join(ROOT, "include")]
+    cmd = ["gcc", "-O1", "-fcommon", "-w", "-DPHOTIC_REFERENCE_TREE", *inc,
+           os.path.join(ROOT, "photic_b200", "host", "samodel_b200.c"), os.path.join(ROOT, "tests", "csrc", "mini_model.c"),
+           os.path.join(REF, "common.c"), "-o", exe, "-L", os.path.dirname(lib), "-lphotic_b200",
+           "-Wl,-rpath," + os.path.dirname(lib), "-lm"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    # the stricter compile of the shim alone must be warning-free too
+    r = subprocess.run(["gcc", "-c", "-fcommon", "-Wall", "-DPHOTIC_REFERENCE_TREE", *inc, "-o", str(tmp_path / "shim.o"),
+                        os.path.join(ROOT, "photic_b200", "host", "samodel_b200.c")], capture_output=True, text=True)
+    own = [l for l in r.stderr.splitlines() if "samodel_b200.c" in l and "warning" in l]
+    assert r.returncode == 0 and not own, r.stderr[-2000:]
+    if not torch.cuda.is_available():
+        run = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+        assert run.returncode == 1 and "ERROR: photic_b200" in run.stdout and "no CPU fallback" in run.stdout
 
 
 @pytest.mark.gpu
@@ -131,6 +164,7 @@ def test_shim_samodel_equals_library(inverter, devices):
             scenes[s].R_sigma[b] = spec.r_sigma
     idx = (C.c_int * ns)(*range(ns))
     os.environ["PHOTIC_B200_SIGMA_SEED"] = "77"  # the reference seeds the depth-error pass with time(NULL)
+    os.environ["PHOTIC_B200_SIGMA_CHAIN"] = "interval"  # one chain per depth interval (the shim's default is the reference's single chain)
     outs = [rows(np.full((R, Cc), 7.0, dtype=np.float32)) for _ in range(10)]
     lib.samodel.restype = None
     lib.samodel.argtypes = [C.POINTER(Scene), C.POINTER(Geogrid), C.POINTER(C.c_int), C.c_int, C.c_int, Geogrid, C.c_int,
@@ -151,3 +185,62 @@ def test_shim_samodel_equals_library(inverter, devices):
         else:
             assert np.array_equal(got.view(np.int32), exp[name].view(np.int32)), name
     assert st["n_valid"] > 50
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("devices", ["", "0,0"])
+def test_c_program_runs_samodel_on_the_device_and_writes_the_reference_files(inverter, tmp_path, devices):
+    """tests/csrc/mini_model.c as a linked C PROGRAM (row-pointer grids, geogrid by value, its own write_nc): the ten
+    grids must equal the library's results bit for bit and write_nc must be called for exactly the files of
+    samodel.c:1513-1687 in the reference's order -- per scene K_coastal, K_blue, K_green, K_red, P, G, X (the _D file
+    is written under DELTA only, which is 0: samodel.c:1586-1596), then modelled_H, H_sigma, error, albedo,
+    bottom_sand, bottom_seagrass, bottom_coral, min_K, bottom_type, index_optical_depth -- with the trimmed scene
+    names (samodel.c:1516) and the geometry of the first grid."""
+    from photic_b200 import build, capi, scene
+    so = build.build_host_shim()
+    exe = _build_mini_model(tmp_path, so)
+    spec = scene.CONFIGS["murion"].scaled(16, 13)
+    planes, prior = scene.generate(spec)
+    planes, prior = planes.numpy(), prior.numpy()
+    R, Cc, ns = spec.nrows, spec.ncols, spec.n_dates
+    fin, fout, flog = (str(tmp_path / n) for n in ("in.bin", "out.bin", "log.txt"))
+    with open(fin, "wb") as f:
+        f.write(np.array([R, Cc, ns], dtype=np.int32).tobytes())
+        f.write(planes.astype(np.float32).tobytes())
+        f.write(prior.astype(np.float32).tobytes())
+    env = {**os.environ, "PHOTIC_B200_SIGMA_SEED": "77", "PHOTIC_B200_SIGMA_CHAIN": "interval"}
+    env.pop("PHOTIC_B200_DEVICES", None)
+    if devices:
+        env["PHOTIC_B200_DEVICES"] = devices
+    r = subprocess.run([exe, fin, fout, flog], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, (r.stdout[-1500:], r.stderr[-1500:])
+    assert "scene 0 is now named 'date0'" in r.stdout          # trim() works in place, as in the reference
+    got = np.fromfile(fout, dtype=np.float32).reshape(10, R, Cc)
+    desc = capi.make_desc(spec.wavelengths, 0.0, [25.0 + 3.0 * s for s in range(ns)], [0.1 * s for s in range(ns)], R, Cc,
+                          r_sigma=1.0e-4)
+    exp, st = inverter.invert_host(desc, planes, prior)
+    sigma, _, _, st2 = inverter.depth_sigma_host(desc, planes, prior, exp["depth"], 77, 128, 1)
+    order = ["depth", None, "model_error", "bottom_albedo", "bottom_sand", "bottom_seagrass", "bottom_coral", "K_min",
+             "bottom_type", "index_optical_depth"]
+    for k, name in enumerate(order):
+        want = sigma if name is None else exp[name]
+        assert np.array_equal(got[k].view(np.int32), want.view(np.int32)), name or "depth_sigma"
+    assert st["n_valid"] > 40 and st2["n_valid"] > 0
+    lines = [l.split() for l in open(flog).read().splitlines()]
+    names = [l[0] for l in lines]
+    want_names = []
+    for s in range(ns):
+        want_names += [f"date{s}_K_{b}.nc" for b in ("coastal", "blue", "green", "red")] + [f"date{s}_{v}.nc" for v in "PGX"]
+    want_names += [f"modelled_{n}.nc" for n in ("H", "H_sigma", "error", "albedo", "bottom_sand", "bottom_seagrass",
+                                                "bottom_coral", "min_K", "bottom_type", "index_optical_depth")]
+    assert names == want_names and len(names) == 7 * ns + 10
+    for l in lines:
+        assert int(l[1]) == Cc and int(l[2]) == R and float(l[3]) == -9999.0
+        assert float(l[5]) == np.float32(100.0 + 30.0 * (Cc - 1)) and float(l[6]) == np.float32(-20.0 + 30.0 * (R - 1))
+    sums = {l[0]: float(l[4]) for l in lines}
+    seq = lambda a: float(np.cumsum(a.ravel().astype(np.float64))[-1])  # noqa: E731  (row-major running sum, as the C loop)
+    assert sums["modelled_H.nc"] == seq(exp["depth"]) and sums["modelled_H_sigma.nc"] == seq(sigma)
+    for s in range(ns):
+        for b, bn in enumerate(("coastal", "blue", "green", "red")):
+            assert sums[f"date{s}_K_{bn}.nc"] == seq(exp["K"][s, b])
+        assert sums[f"date{s}_P.nc"] == seq(exp["P"][s]) and sums[f"date{s}_X.nc"] == seq(exp["X"][s])
