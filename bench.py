@@ -6,12 +6,12 @@
     python bench.py --impl reference ...                               (the reference's CPU code)
 
 Workload (config.workload): BASELINE.json configs[1], the Exmouth-Gulf-shaped 3930x2858, 6-date
-synthetic Landsat-8 scene, cut into `--batches` row batches (default 2: 1965 rows, ~0.77 M valid pixels).
+synthetic Landsat-8 scene, cut into `--batches` row batches (default 4: 983 rows, 1.2 - 1.8 M valid pixels each).
 One STEP inverts one batch -- the SAME raster at every N (strong scaling): at N GPUs the batch is held
 as N equal row bands, one per rank, halo rows are exchanged point to point (NCCL), the solve kernels
 share the work at run time over NVLink (a device that runs out of pixels takes them from its
 neighbours' queues: photic_b200.sharded.BandGroup), and the nine result planes are gathered on rank 0.
-Consecutive steps see different batches (>= 335 MB of reflectance planes each > the 126 MB L2), so
+Consecutive steps see different batches (>= 270 MB of reflectance planes each > the 126 MB L2), so
 nothing is cached between timed iterations.
 
 Printed JSON line (rank 0): `value` = valid pixels inverted / device time with inputs resident in
@@ -47,7 +47,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="exmouth")
-    ap.add_argument("--batches", type=int, default=2,
+    ap.add_argument("--batches", type=int, default=4,
                     help="row batches the scene is cut into; one batch = the raster of one step, at every N")
     ap.add_argument("--no-share", action="store_true", help="N > 1: every rank works on its own band only")
     ap.add_argument("--rows", type=int, default=0, help="debug: shrink the scene")
@@ -182,7 +182,7 @@ def workload_config(spec, args, world, extra=None):
                      f"NBOTTOMS={spec.n_bottoms}, DEPTHS prior",
          "step": f"one batch of {rb} rows x {spec.ncols} cols ({args.batches} batches per scene), the same raster at every "
                  f"GPU count, another batch every step",
-         "l2": "inputs larger than L2: consecutive steps read different batches (>= 335 MB of planes each)",
+         "l2": "inputs larger than L2: consecutive steps read different batches (>= 270 MB of planes each)",
          "parallelism": f"row bands x{world}"}
     if extra:
         c.update(extra)

@@ -11,7 +11,7 @@ namespace phb {
 /* ---- known answers: objective on caller-supplied parameter vectors (one warp) ------------------ */
 template <int SBP>
 __global__ void kat_objective_kernel(const SolveParams p, int nb_active, int n_regions, int origin,
-                                     const double *meas, int nvec, const double *params, double *out6) {
+                                     const double *meas, int nvec, const double *params, double *out6, int generic) {
   const ModelConst &M = *p.M;
   stage_cta(p, M, phb_smem);
   __syncthreads();
@@ -33,7 +33,11 @@ __global__ void kat_objective_kernel(const SolveParams p, int nb_active, int n_r
   for (int v = 0; v < nvec; v++) {
     for (int i = lane; i < px.n; i += 32) w.xmin[i] = params[(size_t)v * px.n + i];
     __syncwarp();
-    const double e = objective<0, SBP, true>(w, px, lane, SB, Ns, p.L.NbMax, w.xmin, side);
+    /* the instantiation the solve kernel uses for this substrate count: the compile-time classes for 3 and 1 */
+    double e;
+    if (!generic && nb_active == 3 && n_regions <= 16) e = objective<3, SBP, true>(w, px, lane, SB, Ns, p.L.NbMax, w.xmin, side);
+    else if (!generic && nb_active == 1 && n_regions <= 16) e = objective<1, SBP, true>(w, px, lane, SB, Ns, p.L.NbMax, w.xmin, side);
+    else e = objective<0, SBP, true>(w, px, lane, SB, Ns, p.L.NbMax, w.xmin, side);
     if (lane == 0) {
       double *o = out6 + (size_t)v * 6;
       o[0] = e; o[1] = side.e_rrs; o[2] = side.e_depth; o[3] = side.e_bottom; o[4] = side.e_K; o[5] = side.bottom_albedo;

@@ -234,6 +234,8 @@ void view_pointers(BandView &v, const void **slots[23]) {
 
 bool use_two_classes(const ModelConst &M) {
   if (M.n_bottoms != 3) return false; /* the default NBOTTOMS has the compile-time instantiations */
+  const int nsp = M.n_spatial == 0 ? 1 : M.n_spatial;
+  if ((2 * nsp - 1) * (2 * nsp - 1) > 16) return false; /* ... written for up to 16 regions (NSPATIAL <= 2, the default) */
   const char *e = getenv("PHB_ONE_CLASS");
   return !(e && atoi(e) != 0);
 }
@@ -372,9 +374,9 @@ static int launch_solve(phb_ctx *c, const ModelConst &M, SolveParams &sp, bool t
    * by the one-substrate code for the sand-only queue), run-time loop otherwise; compile-time (scene,band) stride 32
    * (up to 8 dates x 4 bands) or the maximum */
   void (*kern)(const SolveParams) = sp.L.SBP == 32 ? solve_kernel<0, 32, false> : solve_kernel<0, kMaxSB, false>;
-  if (M.n_bottoms == 3) kern = sp.L.SBP == 32 ? solve_kernel<3, 32, false> : solve_kernel<3, kMaxSB, false>; /* the default NBOTTOMS */
+  if (trials || !use_two_classes(M)) sp.n_classes = 1;
+  if (sp.n_classes == 2) kern = sp.L.SBP == 32 ? solve_kernel<3, 32, false> : solve_kernel<3, kMaxSB, false>; /* the default NBOTTOMS */
   if (trials) kern = sp.L.SBP == 32 ? solve_kernel<0, 32, true> : solve_kernel<0, kMaxSB, true>;
-  if (trials || M.n_bottoms != 3) sp.n_classes = 1;
   cudaFuncAttributes fa0;
   CK(cudaFuncGetAttributes(&fa0, kern));
   const int W_reg = fa0.maxThreadsPerBlock / 32;
@@ -1491,10 +1493,11 @@ int phb_kat_objective(phb_ctx *c, const phb_scene_desc *desc, int nb_active, int
   CK(cudaMemcpy(d_meas, flat.data(), nm * 8, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(d_par, params, (size_t)nvec * nparams * 8, cudaMemcpyHostToDevice));
   const size_t smem = (size_t)sp.L.cta_bytes + sp.L.warp_bytes;
-  void (*kk)(const SolveParams, int, int, int, const double *, int, const double *, double *) =
+  void (*kk)(const SolveParams, int, int, int, const double *, int, const double *, double *, int) =
       sp.L.SBP == 32 ? kat_objective_kernel<32> : kat_objective_kernel<kMaxSB>;
   CK(cudaFuncSetAttribute(kk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kk<<<1, 32, smem>>>(sp, nb_active, n_regions, origin, d_meas, nvec, d_par, d_out);
+  const char *e_gen = getenv("PHB_ONE_CLASS"); /* the run-time-substrate-count instantiation for every count */
+  kk<<<1, 32, smem>>>(sp, nb_active, n_regions, origin, d_meas, nvec, d_par, d_out, (e_gen && atoi(e_gen) != 0) ? 1 : 0);
   CK(cudaGetLastError());
   CK(cudaMemcpy(out6, d_out, (size_t)nvec * 6 * 8, cudaMemcpyDeviceToHost));
   cudaFree(d_meas); cudaFree(d_par); cudaFree(d_out);

@@ -148,7 +148,11 @@ void kat_objective_body() {
   for (int v = 0; v < g_kat.nvec; v++) {
     for (int i = lane; i < px.n; i += 32) w.xmin[i] = g_kat.params[(size_t)v * px.n + i];
     __syncwarp();
-    const double e = objective<0, SBP, true>(w, px, lane, SB, Ns, p.L.NbMax, w.xmin, side);
+    const bool generic = getenv("PHB_ONE_CLASS") != nullptr;
+    double e; /* as kat_objective_kernel: the compile-time classes for 3 and 1 substrates */
+    if (!generic && px.Nb == 3 && px.Nr <= 16) e = objective<3, SBP, true>(w, px, lane, SB, Ns, p.L.NbMax, w.xmin, side);
+    else if (!generic && px.Nb == 1 && px.Nr <= 16) e = objective<1, SBP, true>(w, px, lane, SB, Ns, p.L.NbMax, w.xmin, side);
+    else e = objective<0, SBP, true>(w, px, lane, SB, Ns, p.L.NbMax, w.xmin, side);
     if (lane == 0) {
       double *o = g_kat.out6 + (size_t)v * 6;
       o[0] = e; o[1] = side.e_rrs; o[2] = side.e_depth; o[3] = side.e_bottom; o[4] = side.e_K; o[5] = side.bottom_albedo;
@@ -169,7 +173,8 @@ struct EmuBand {
     using namespace phb;
     memset(&view, 0, sizeof(view));
     view.planes = planes; view.prior = M.prior_present ? prior : nullptr; view.nrows = M.nrows; view.out = out;
-    two = M.n_bottoms == 3 && getenv("PHB_ONE_CLASS") == nullptr;
+    const int nsp_ = M.n_spatial == 0 ? 1 : M.n_spatial;
+    two = M.n_bottoms == 3 && (2 * nsp_ - 1) * (2 * nsp_ - 1) <= 16 && getenv("PHB_ONE_CLASS") == nullptr; /* photic_b200.cu: use_two_classes */
     q0.clear(); q1.clear();
     for (int k = 0; k < n_queue; k++) {
       bool deep = false;
@@ -331,7 +336,7 @@ int emu_invert_raster(const void *model, int64_t model_size, const float *planes
   EmuBand band; /* the device's two lists as classify_kernel left them (their concatenation for the generic kernel) */
   memset(&band.view, 0, sizeof(band.view));
   band.view.planes = planes; band.view.prior = cp.prior; band.view.nrows = M.nrows; band.view.out = o;
-  band.two = M.n_bottoms == 3 && getenv("PHB_ONE_CLASS") == nullptr;
+  band.two = M.n_bottoms == 3 && (2 * nsp - 1) * (2 * nsp - 1) <= 16 && getenv("PHB_ONE_CLASS") == nullptr;
   if (band.two) {
     band.view.queue[0] = q_shallow.data(); band.view.n_queue[0] = &scal[0]; band.view.head[0] = &band.scal[3];
     band.view.queue[1] = q_deep.data(); band.view.n_queue[1] = &scal[1]; band.view.head[1] = &band.scal[4];

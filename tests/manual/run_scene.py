@@ -6,9 +6,11 @@
         tests/manual/run_scene.py --config pilbara [--refine]                            (8 GPUs)
 
 Every rank starts with an equal split of the scene's rows resident in HBM (synthetic, generated in place). Timed:
-cost estimate + all-reduce -> cost-balanced row bands -> rows re-dealt point-to-point (NCCL over NVLink) -> halo
-exchange -> per-band inversion (no collective on the data path) -> [REFINE with all-reduced min/max] -> gather of the
-nine result planes on rank 0. Rank 0 prints one JSON line (also written to gpurun_out/ when that directory exists).
+halo exchange between neighbouring bands (NCCL point to point over NVLink) -> the band's rasters into its shareable
+allocation -> validity scan + work queues -> per-band inversion, every device taking pixels from its neighbours' queues
+once its own is empty (no collective and no cost model on the data path) -> [REFINE with all-reduced min/max] -> gather
+of the nine result planes on rank 0. --no-share: cost-balanced contiguous bands (round 1), every rank on its own band.
+Rank 0 prints one JSON line (also written to gpurun_out/ when that directory exists).
 """
 import argparse, json, os, sys, time
 import numpy as np
@@ -25,6 +27,8 @@ ap.add_argument("--rows", type=int, default=0)
 ap.add_argument("--cols", type=int, default=0)
 ap.add_argument("--refine", action="store_true", help="REFINE SCALE+POWER on the depth plane (global min/max all-reduced)")
 ap.add_argument("--check", type=int, default=0, help="pixels per rank to check against the CPU oracle (bit equality)")
+ap.add_argument("--no-share", action="store_true", help="round-1 path: cost-balanced bands, no work sharing")
+ap.add_argument("--tag", default="")
 args = ap.parse_args()
 
 world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -50,25 +54,33 @@ ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
 torch.cuda.synchronize()
 wall0 = time.time()
 ev[0].record()
-# 1. cost estimate -> balanced bands
-cost = torch.zeros(spec.nrows, device=dev)
-cost[e0:e1] = sharded.row_cost_from_prior(scene.valid_mask(planes_eq), prior_eq)
-if world > 1:
-    dist.all_reduce(cost)
-plan = sharded.plan_row_bands(cost.cpu().numpy(), world)
+if args.no_share:
+    # 1. cost estimate -> balanced bands; 2. re-deal rows
+    cost = torch.zeros(spec.nrows, device=dev)
+    cost[e0:e1] = sharded.row_cost_from_prior(scene.valid_mask(planes_eq), prior_eq)
+    if world > 1:
+        dist.all_reduce(cost)
+    plan = sharded.plan_row_bands(cost.cpu().numpy(), world)
+    planes = sharded.repartition_rows(planes_eq, eq, plan, rank, world)
+    prior = sharded.repartition_rows(prior_eq[None], eq, plan, rank, world)[0]
+else:
+    plan, planes, prior = eq, planes_eq, prior_eq   # equal rows: the devices share the work at run time
 r0, r1 = plan[rank]
-# 2. re-deal rows, exchange halo rows
-planes = sharded.repartition_rows(planes_eq, eq, plan, rank, world)
-prior = sharded.repartition_rows(prior_eq[None], eq, plan, rank, world)[0]
 del planes_eq, prior_eq
-win = sharded.exchange_halo(planes, plan, halo, rank, world)
-prw = sharded.exchange_halo(prior[None], plan, halo, rank, world)[0]
 w0, w1, lb, le = sharded.window(r0, r1, halo, spec.nrows)
-ev[1].record()
-# 3. inversion of this band
 desc = capi.desc_from_spec(spec, nrows=w1 - w0)
-outs = Inverter.alloc_device_outputs(desc, dev, scene_planes=False)
-st = inv.invert_device(desc, win.contiguous(), prw.contiguous(), outs, row_begin=lb, row_end=le)
+group = sharded.BandGroup(inv, desc, lb, le, rank, world, share=not args.no_share)   # allocation + handle exchange
+band = group.band
+# 2. halo rows from the neighbouring bands, straight into the band's rasters
+band.planes.copy_(sharded.exchange_halo(planes, plan, halo, rank, world))
+band.prior.copy_(sharded.exchange_halo(prior[None], plan, halo, rank, world)[0])
+win, prw = band.planes, band.prior
+del planes, prior
+ev[1].record()
+# 3. inversion of this band (+ pixels of the neighbours' bands once its own queue is empty)
+st = group.step()
+own_valid = band.valid()
+outs = band.outputs
 ev[2].record()
 # 4. optional REFINE on the depth plane (refine.c:215-301): global min/max over all bands
 if args.refine:
@@ -96,8 +108,14 @@ if world > 1:
 wall = time.time() - wall0
 ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(4)]
 t = torch.tensor([ev[0].elapsed_time(ev[4]), ms[0], ms[1], ms[2], ms[3], st["ms_solve"]], dtype=torch.float64, device=dev)
-agg = torch.tensor([float(st["n_valid"]), st["alg_flops"], float(st["n_evals"]), float(st["n_converged"]), float(st["n_shallow"])],
-                   dtype=torch.float64, device=dev)
+agg = torch.tensor([float(st["n_valid"]), st["alg_flops"], float(st["n_evals"]), float(st["n_converged"]), float(st["n_shallow"]),
+                    float(own_valid)], dtype=torch.float64, device=dev)
+share_t = torch.tensor([float(st["n_valid"]) - float(own_valid)], dtype=torch.float64, device=dev)  # pixels taken from (+) / given to (-) neighbours
+share_all = [torch.zeros_like(share_t) for _ in range(world)]
+if world > 1:
+    dist.all_gather(share_all, share_t)
+else:
+    share_all = [share_t]
 tmin = t.clone()
 if world > 1:
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -122,6 +140,7 @@ if rank == 0:
     total_ms = float(t[0]); npx = float(agg[0])
     line = {"what": "whole scene, sharded", "config": args.config, "scene": f"{spec.nrows}x{spec.ncols}, {spec.n_dates} dates", "n_gpus": world,
             "valid_pixels": int(npx), "px_per_s": npx / (total_ms * 1e-3), "seconds_device": total_ms * 1e-3, "seconds_wall": wall,
+            "work_sharing": bool(st.get("shared", False)), "pixels_taken_from_neighbours_per_rank": [int(x[0]) for x in share_all],
             "phases_ms_max_over_ranks": {"plan+redeal+halo": float(t[1]), "invert": float(t[2]), "refine": float(t[3]), "gather": float(t[4]),
                                          "solve_kernel": float(t[5])},
             "solve_kernel_ms_min_over_ranks": float(tmin[5]), "band_balance": float(tmin[5]) / float(t[5]),
@@ -132,7 +151,7 @@ if rank == 0:
             "oracle_check_bit_identical": ok, "scene_generation_s": t_gen, "plan": plan}
     print(json.dumps(line))
     if os.path.isdir(os.path.join(ROOT, "gpurun_out")):
-        with open(os.path.join(ROOT, "gpurun_out", f"scene_{args.config}_n{world}.json"), "w") as f:
+        with open(os.path.join(ROOT, "gpurun_out", f"scene_{args.config}_n{world}{args.tag}.json"), "w") as f:
             f.write(json.dumps(line) + "\n")
 if world > 1:
     dist.barrier()

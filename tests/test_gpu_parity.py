@@ -210,9 +210,14 @@ def test_full_size_exmouth_sampled_against_oracle(inverter, oracle_port):
     assert np.array_equal(got["n_evals"], ref["n_evals"]) and np.array_equal(got["converged"], ref["converged"].astype(np.uint8))
 
 
-def test_objective_known_answers_on_device(inverter):
-    """samodel_error / samodel_Rrs on random parameter vectors: reference's own outputs (golden)."""
+@pytest.mark.parametrize("generic", [False, True])
+def test_objective_known_answers_on_device(inverter, generic, monkeypatch):
+    """samodel_error / samodel_Rrs on random parameter vectors: reference's own outputs (golden). Through the
+    instantiation the solve kernel uses for the substrate count (compile-time classes for 3 and 1) and, generic, through
+    the run-time-count instantiation for every count (PHB_ONE_CLASS=1)."""
     from photic_b200 import capi, scene
+    if generic:
+        monkeypatch.setenv("PHB_ONE_CLASS", "1")
     k = load_golden("kat_objective")
     for tag in "abcd":
         ns, nb, nr, origin = (int(v) for v in k[f"{tag}_meta"])
@@ -221,11 +226,14 @@ def test_objective_known_answers_on_device(inverter):
         assert bits_equal(got, k[f"{tag}_out"]).all(), tag
 
 
-def test_objective_extreme_parameters_take_the_fallback_paths(inverter):
+@pytest.mark.parametrize("generic", [False, True])
+def test_objective_extreme_parameters_take_the_fallback_paths(inverter, generic, monkeypatch):
     """Parameter vectors outside the guaranteed range of the branch-free division / sqrt / exp (H = 0, 1e-300, 150 m,
     1e300; zero, tiny and huge IOPs and albedos; 0/0 mixing weights; inf and NaN coordinates), in all or only some
     regions so that fallback lanes sit next to fast-path lanes: still the reference's bits, NaNs where it has NaNs."""
     from photic_b200 import capi, scene
+    if generic:
+        monkeypatch.setenv("PHB_ONE_CLASS", "1")
     k = load_golden("kat_objective_extreme")
     for tag in "abc":
         ns, nb, nr, origin = (int(v) for v in k[f"{tag}_meta"])

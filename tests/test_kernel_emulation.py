@@ -78,12 +78,17 @@ def test_emulated_kernel_without_depth_prior(emu, oracle_port):
     _check(emu, oracle_port, "murion", 8, 8, {}, 2, 4096, use_prior=False)
 
 
-@pytest.mark.parametrize("define", ["", "PHB_PIPELINE_TERMS=1", "PHB_COLD_OUT=1"])
-def test_emulated_objective_known_answers(product_lib, define):
+@pytest.mark.parametrize("define", ["", "PHB_PIPELINE_TERMS=1", "PHB_COLD_OUT=1", "generic", "PHB_UNIFIED_PENALTY=0"])
+def test_emulated_objective_known_answers(product_lib, define, monkeypatch):
     """samodel_error of the kernel source on the reference's own known answers (tests/golden/kat_objective*.npz),
-    including the extreme parameter vectors that send lanes through the out-of-range fallbacks."""
+    including the extreme parameter vectors that send lanes through the out-of-range fallbacks. Each substrate count
+    runs through the instantiation the solve kernel uses for it (compile-time classes for 3 and 1, where the sand-only
+    class takes the depth and substrate penalties in one pass); "generic": the run-time-count code for every count."""
     from conftest import load_golden
     from photic_b200 import capi, scene
+    if define == "generic":
+        monkeypatch.setenv("PHB_ONE_CLASS", "1")
+        define = ""
     e = Emulator((define,), tag=define.split("=")[0].lower()) if define else Emulator()
     for gname, tags in (("kat_objective", "abcd"), ("kat_objective_extreme", "abc")):
         k = load_golden(gname)
