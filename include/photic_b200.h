@@ -277,6 +277,25 @@ int phb_refine_host(phb_ctx *ctx, const float *h_in, float nodata, const float *
                     float *h_out);
 
 /*
+ * int16 scale/offset packing of a grid, the form every photic grid takes in its NetCDF file:
+ * compress_2d (model/nc.c:271-320, called by write_nc nc.c:14) and decompress_2d (nc.c:247-266, called by read_nc
+ * nc.c:138). Packing on the device before the copy to the host halves the bytes that cross PCIe; NetCDF I/O itself stays
+ * on the host. Bit-identical to the reference including its order-dependent range (the running maximum starts at
+ * FLT_MIN and is only tested when a value did not lower the running minimum, nc.c:286-298) and the x86 `(short) rint()`.
+ *   pack    add_offset = the minimum, scale_factor = (max - min) / 32767, missing_value = SHRT_MIN, cells == (float)spval
+ *           -> missing_value. Synchronises the stream once (two floats come back before the packing pass).
+ *   unpack  missing_value -> (float)spval, else (float)packed * scale_factor + add_offset.
+ */
+int phb_nc_pack_device(phb_ctx *ctx, const float *d_grid, int64_t n, double spval, int16_t *d_packed, float *add_offset,
+                       float *scale_factor, int16_t *missing_value, void *stream);
+int phb_nc_unpack_device(phb_ctx *ctx, const int16_t *d_packed, int64_t n, float add_offset, float scale_factor,
+                         int16_t missing_value, double spval, float *d_grid, void *stream);
+int phb_nc_pack_host(phb_ctx *ctx, const float *h_grid, int nrows, int ncols, double spval, int16_t *h_packed,
+                     float *add_offset, float *scale_factor, int16_t *missing_value);
+int phb_nc_unpack_host(phb_ctx *ctx, const int16_t *h_packed, int nrows, int ncols, float add_offset, float scale_factor,
+                       int16_t missing_value, double spval, float *h_grid);
+
+/*
  * MODEL Lee_Kd_LS8 / MODEL Lee_Secchi_LS8 (bam.c:3250-3610 -> Kd_LS8 secchi.c:13, secchi_disk_depth secchi.c:59):
  * Lee et al. (2016) diffuse attenuation (mode 0: min over Kd(443,481,530,554,656)) and Secchi-disk depth (mode 1)
  * from the coastal / blue / green / red Landsat-8 reflectance planes; these feed the scene-level priors upstream

@@ -199,6 +199,24 @@ class Oracle:
                             _p(sp, _fp), C.c_float(theta_s), _p(out, _fp))
         return out
 
+    def nc_pack(self, grid, spval):
+        """compress_2d (nc.c:271-320): int16 packing of a float grid. Returns (packed int16, add_offset, scale_factor, missing)."""
+        grid = _f(grid)
+        packed = np.zeros(grid.shape, dtype=np.int16)
+        os2 = np.zeros(2, dtype=np.float32)
+        miss = C.c_short(0)
+        self._fn("nc_pack")(C.c_int(grid.shape[0]), C.c_int(grid.shape[1]), _p(grid, _fp), C.c_double(spval),
+                             packed.ctypes.data_as(C.c_void_p), _p(os2, _fp), C.byref(miss))
+        return packed, os2[0], os2[1], int(miss.value)
+
+    def nc_unpack(self, packed, add_offset, scale_factor, missing, spval):
+        """decompress_2d (nc.c:247-266)."""
+        packed = np.ascontiguousarray(packed, dtype=np.int16)
+        out = np.zeros(packed.shape, dtype=np.float32)
+        self._fn("nc_unpack")(C.c_int(packed.shape[0]), C.c_int(packed.shape[1]), packed.ctypes.data_as(C.c_void_p),
+                               C.c_float(add_offset), C.c_float(scale_factor), C.c_short(missing), C.c_double(spval), _p(out, _fp))
+        return out
+
     def refine(self, grid, nodata, land, land_nodata, shallow, shallow_nodata, flags, args):
         """REFINE: pho_refine (restatement) or ref_refine (the reference's own run_refine(), refine.c:12-302)."""
         grid = _f(grid)

@@ -12,6 +12,8 @@
  */
 #include "photic_oracle.h"
 
+#include <float.h>
+#include <limits.h>
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -1108,6 +1110,53 @@ int pho_lee_ls8(int mode, int nrows, int ncols, const float *coastal, const floa
       if (red[q] > mx) mx = red[q];
       out[q] = log(fabs(0.14 - mx) / 0.013) / (2.5 * kmin);
     }
+  }
+  return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * int16 scale/offset packing of a grid for NetCDF (row N4): compress_2d model/nc.c:271-320 and
+ * decompress_2d model/nc.c:247-266, restated on flat arrays.
+ *
+ * Quirks kept (nc.c:287-301): the running maximum starts at FLT_MIN (the smallest positive float, not -FLT_MAX) and
+ * sits in the `else` of the running-minimum test, so a value that lowers the minimum when it is met -- the first value
+ * always does -- never raises the maximum; the range is therefore order dependent. The short is (short)rint(.) of a
+ * FLOAT quotient: on x86-64 that is cvttsd2si to 32 bits (INT_MIN for NaN / out of range) and the low 16 bits of it.
+ * ------------------------------------------------------------------------------------------------ */
+static short pho_to_short_x86(double v) {
+  int w;
+  if (!(fabs(v) < 2147483648.0)) w = (int)0x80000000u; /* cvttsd2si: indefinite integer */
+  else w = (int)v;
+  return (short)(unsigned short)((unsigned)w & 0xffffu);
+}
+
+int pho_nc_pack(int nrows, int ncols, const float *grid, double spval, short *packed, float *offset_scale, short *missing) {
+  const long n = (long)nrows * ncols;
+  const float fspv = (float)spval;               /* nc.c:278 */
+  float grmin = FLT_MAX, grmax = FLT_MIN;        /* nc.c:286-287 */
+  for (long k = 0; k < n; k++) {                 /* nc.c:289-298, row-major */
+    const float v = grid[k];
+    if (v == fspv) continue;
+    if (v < grmin) grmin = v;
+    else if (v > grmax) grmax = v;
+  }
+  const float scale = (grmax - grmin) / ((float)SHRT_MAX); /* nc.c:306 */
+  *missing = SHRT_MIN;                           /* nc.c:282 */
+  offset_scale[0] = grmin; offset_scale[1] = scale;
+  for (long k = 0; k < n; k++) {                 /* nc.c:311-318 */
+    const float v = grid[k];
+    if (v == fspv) packed[k] = SHRT_MIN;
+    else { const float q = (v - grmin) / scale; packed[k] = pho_to_short_x86(rint((double)q)); }
+  }
+  return 0;
+}
+
+int pho_nc_unpack(int nrows, int ncols, const short *packed, float add_offset, float scale_factor, short missing,
+                  double spval, float *grid) {
+  const long n = (long)nrows * ncols;
+  for (long k = 0; k < n; k++) {                 /* nc.c:254-264 */
+    if (packed[k] == missing) grid[k] = (float)spval;
+    else { const float t = ((float)packed[k]) * scale_factor; grid[k] = t + add_offset; }
   }
   return 0;
 }

@@ -127,6 +127,12 @@ def lib() -> C.CDLL:
         L.phb_depth_sigma_rows.argtypes = [C.c_void_p, C.POINTER(SceneDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint,
                                            C.c_int, C.c_int, C.c_int, C.c_void_p, _dp, C.POINTER(C.c_int32), _dp,
                                            C.POINTER(Stats)]
+        L.phb_nc_pack_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_void_p, _fp, _fp,
+                                         C.POINTER(C.c_int16), C.c_void_p]
+        L.phb_nc_unpack_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_float, C.c_int16, C.c_double,
+                                           C.c_void_p, C.c_void_p]
+        L.phb_nc_pack_host.argtypes = [C.c_void_p, _fp, C.c_int, C.c_int, C.c_double, C.c_void_p, _fp, _fp, C.POINTER(C.c_int16)]
+        L.phb_nc_unpack_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int16, C.c_double, _fp]
         L.phb_plan_row_bands.argtypes = [C.POINTER(SceneDesc), C.POINTER(C.c_void_p), C.c_void_p, C.c_int,
                                          C.POINTER(C.c_int32), _dp]
         L.phb_invert_host_multi.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.POINTER(SceneDesc), C.POINTER(C.c_void_p),
@@ -162,7 +168,8 @@ EXPORTS = ["phb_version", "phb_error_string", "phb_device_count", "phb_ctx_creat
            "phb_jerlov_fit", "phb_jerlov_k", "phb_jerlov_k_from_ratio",
            "phb_plan_row_bands", "phb_invert_host_multi", "phb_debug_model_const", "phb_invert_rows",
            "phb_shard_create", "phb_shard_buffers", "phb_shard_export", "phb_shard_prepare", "phb_shard_solve",
-           "phb_shard_valid", "phb_shard_destroy", "phb_depth_sigma_rows"]
+           "phb_shard_valid", "phb_shard_destroy", "phb_depth_sigma_rows",
+           "phb_nc_pack_device", "phb_nc_unpack_device", "phb_nc_pack_host", "phb_nc_unpack_host"]
 
 
 def check(rc: int) -> None:

@@ -187,6 +187,127 @@ __global__ void refine_minmax_kernel(const float *in, long long n, float nodata,
   if ((threadIdx.x & 31) == 0) { atomicMin(mm + 0, lo); atomicMax(mm + 1, hi); }
 }
 
+/* ---- int16 scale/offset packing of a grid for NetCDF (row N4): compress_2d / decompress_2d, model/nc.c:247-320 ----
+ * The reference finds the range in ONE sequential pass whose maximum test sits in the `else` of the minimum test and
+ * starts at FLT_MIN (nc.c:286-298): a value that lowers the running minimum when it is met never raises the maximum,
+ * so the range depends on the ORDER of the cells. Reproduced exactly in three passes over the row-major cells cut into
+ * chunks of kPackChunk: (1) the minimum of every chunk, (2) an exclusive prefix-minimum over the chunks (one block),
+ * (3) every chunk again, each thread walking 16 consecutive cells from the running minimum that reaches it (exclusive
+ * prefix over the threads of the block, seeded with the chunk's carry) and keeping the largest value that did not lower
+ * it; then the packing pass. All four are bandwidth-bound: 4 + 4 + 4 B read and 2 B written per cell. */
+constexpr int kPackThreads = 256, kPackPer = 16, kPackChunk = kPackThreads * kPackPer;
+__device__ __forceinline__ float run_min(float a, float v) { return v < a ? v : a; } /* `if (v < grmin) grmin = v`; NaN never lowers it */
+
+__global__ void nc_chunk_min_kernel(const float *in, long long n, float fspv, float *chunk_min, int n_chunks) {
+  __shared__ float wm[kPackThreads / 32];
+  for (int ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
+    const long long base = (long long)ch * kPackChunk;
+    float m = 3.402823466e+38f; /* FLT_MAX */
+#pragma unroll 4
+    for (int q = 0; q < kPackPer; q++) {
+      const long long i = base + q * kPackThreads + threadIdx.x;
+      if (i < n) { const float v = __ldg(in + i); if (!(v == fspv)) m = run_min(m, v); }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = run_min(m, __shfl_xor_sync(kFull, m, o));
+    if ((threadIdx.x & 31) == 0) wm[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = wm[0];
+      for (int k = 1; k < kPackThreads / 32; k++) t = run_min(t, wm[k]);
+      chunk_min[ch] = t;
+    }
+    __syncthreads();
+  }
+}
+
+/* in place: chunk_min[k] <- min(FLT_MAX, chunk_min[0..k-1]); total[0] <- the minimum of everything. One block. */
+__global__ void nc_chunk_scan_kernel(float *chunk_min, int n_chunks, float *total) {
+  __shared__ float part[1024];
+  const int T = blockDim.x, per = (n_chunks + T - 1) / T;
+  const int a = threadIdx.x * per, b = a + per < n_chunks ? a + per : n_chunks;
+  float m = 3.402823466e+38f;
+  for (int k = a; k < b; k++) m = run_min(m, chunk_min[k]);
+  part[threadIdx.x] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) { /* exclusive prefix over <= 1024 partials */
+    float run = 3.402823466e+38f;
+    for (int k = 0; k < T; k++) { const float v = part[k]; part[k] = run; run = run_min(run, v); }
+    total[0] = run;
+  }
+  __syncthreads();
+  float run = part[threadIdx.x];
+  for (int k = a; k < b; k++) { const float v = chunk_min[k]; chunk_min[k] = run; run = run_min(run, v); }
+}
+
+__global__ void nc_chunk_max_kernel(const float *in, long long n, float fspv, const float *carry, int n_chunks,
+                                    unsigned int *grmax_ordered) {
+  __shared__ float cell[kPackChunk];
+  __shared__ float wpre[kPackThreads / 32];
+  float best = 1.175494351e-38f; /* FLT_MIN, nc.c:287 */
+  for (int ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
+    const long long base = (long long)ch * kPackChunk;
+    for (int q = 0; q < kPackPer; q++) { /* coalesced load; cells past the end behave like the missing value */
+      const long long i = base + q * kPackThreads + threadIdx.x;
+      cell[q * kPackThreads + threadIdx.x] = i < n ? __ldg(in + i) : fspv;
+    }
+    __syncthreads();
+    const float *mine = cell + threadIdx.x * kPackPer; /* 16 consecutive cells */
+    float m = 3.402823466e+38f;
+#pragma unroll
+    for (int q = 0; q < kPackPer; q++) { const float v = mine[q]; if (!(v == fspv)) m = run_min(m, v); }
+    /* exclusive prefix minimum over the threads of the block, in thread order */
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    float inc = m;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const float t = __shfl_up_sync(kFull, inc, o); if (lane >= o) inc = run_min(inc, t); }
+    if (lane == 31) wpre[wid] = inc;
+    __syncthreads();
+    float run = carry[ch];
+    for (int k = 0; k < wid; k++) run = run_min(run, wpre[k]);
+    const float before = __shfl_up_sync(kFull, inc, 1);
+    if (lane > 0) run = run_min(run, before);
+    /* the reference's loop body on this thread's cells (nc.c:291-297) */
+#pragma unroll
+    for (int q = 0; q < kPackPer; q++) {
+      const float v = mine[q];
+      if (v == fspv) continue;
+      if (v < run) run = v;
+      else if (v > best) best = v;
+    }
+    __syncthreads();
+  }
+  unsigned int o = float_to_ordered(best);
+  o = __reduce_max_sync(kFull, o);
+  if ((threadIdx.x & 31) == 0) atomicMax(grmax_ordered, o);
+}
+
+/* (short) rint(.) as x86-64 does it: cvttsd2si to 32 bits (INT_MIN for NaN / out of range), low 16 bits */
+__device__ __forceinline__ short to_short_x86(double v) {
+  int w;
+  if (!(fabs(v) < 2147483648.0)) w = (int)0x80000000u;
+  else w = __double2int_rz(v);
+  return (short)(unsigned short)((unsigned)w & 0xffffu);
+}
+
+__global__ void nc_pack_kernel(const float *in, long long n, float fspv, float grmin, float scale, short *out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = __ldg(in + i);
+    short r;
+    if (v == fspv) r = (short)-32768; /* SHRT_MIN, nc.c:282,314 */
+    else { const float q = __fdiv_rn(__fsub_rn(v, grmin), scale); r = to_short_x86(rint((double)q)); } /* nc.c:316 */
+    out[i] = r;
+  }
+}
+
+__global__ void nc_unpack_kernel(const short *in, long long n, float add_offset, float scale_factor, short missing,
+                                 float fspv, float *out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const short c = in[i];
+    out[i] = (c == missing) ? fspv : __fadd_rn(__fmul_rn((float)c, scale_factor), add_offset); /* nc.c:259-262 */
+  }
+}
+
 struct RefineParams {
   const float *in, *land, *shallow;
   float *out;

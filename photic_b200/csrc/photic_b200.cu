@@ -1575,6 +1575,82 @@ int phb_refine_host(phb_ctx *c, const float *h_in, float nodata, const float *h_
   return PHB_OK;
 }
 
+/* ---- int16 scale/offset packing (model/nc.c:247-320) ------------------------------------------------------------ */
+
+int phb_nc_pack_device(phb_ctx *c, const float *d_grid, int64_t n, double spval, int16_t *d_packed, float *add_offset,
+                       float *scale_factor, int16_t *missing_value, void *stream) {
+  if (!c || !d_grid || !d_packed || !add_offset || !scale_factor || n <= 0) return PHB_EINVAL;
+  CK(cudaSetDevice(c->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const float fspv = (float)spval;
+  const long long n_chunks_ll = (n + kPackChunk - 1) / kPackChunk;
+  if (n_chunks_ll > 2147483647LL) return PHB_EINVAL;
+  const int n_chunks = (int)n_chunks_ll;
+  CK(c->outs.ensure((size_t)n_chunks + 4));
+  float *chunk = c->outs.p, *d_min = c->outs.p + n_chunks;
+  unsigned int *d_max = reinterpret_cast<unsigned int *>(c->outs.p + n_chunks + 1);
+  const unsigned int init = float_to_ordered(1.175494351e-38f); /* FLT_MIN, nc.c:287 */
+  CK(cudaMemcpyAsync(d_max, &init, sizeof(init), cudaMemcpyHostToDevice, st));
+  const int blocks = n_chunks < c->n_sm * 8 ? n_chunks : c->n_sm * 8;
+  nc_chunk_min_kernel<<<blocks, kPackThreads, 0, st>>>(d_grid, (long long)n, fspv, chunk, n_chunks);
+  nc_chunk_scan_kernel<<<1, 1024, 0, st>>>(chunk, n_chunks, d_min);
+  nc_chunk_max_kernel<<<blocks, kPackThreads, 0, st>>>(d_grid, (long long)n, fspv, chunk, n_chunks, d_max);
+  CK(cudaGetLastError());
+  float grmin;
+  unsigned int mx;
+  CK(cudaMemcpyAsync(&grmin, d_min, sizeof(float), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(&mx, d_max, sizeof(mx), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  const float grmax = ordered_to_float(mx);
+  volatile float span = grmax - grmin;           /* nc.c:306: float arithmetic */
+  volatile float scale = span / 32767.0f;
+  *add_offset = grmin; *scale_factor = scale;
+  if (missing_value) *missing_value = (int16_t)-32768;
+  nc_pack_kernel<<<c->n_sm * 8, 256, 0, st>>>(d_grid, (long long)n, fspv, grmin, scale, d_packed);
+  CK(cudaGetLastError());
+  return PHB_OK;
+}
+
+int phb_nc_unpack_device(phb_ctx *c, const int16_t *d_packed, int64_t n, float add_offset, float scale_factor,
+                         int16_t missing_value, double spval, float *d_grid, void *stream) {
+  if (!c || !d_packed || !d_grid || n <= 0) return PHB_EINVAL;
+  CK(cudaSetDevice(c->device));
+  nc_unpack_kernel<<<c->n_sm * 8, 256, 0, (cudaStream_t)stream>>>(d_packed, (long long)n, add_offset, scale_factor, missing_value,
+                                                                  (float)spval, d_grid);
+  CK(cudaGetLastError());
+  return PHB_OK;
+}
+
+int phb_nc_pack_host(phb_ctx *c, const float *h_grid, int nrows, int ncols, double spval, int16_t *h_packed,
+                     float *add_offset, float *scale_factor, int16_t *missing_value) {
+  if (!c || !h_grid || !h_packed || nrows < 1 || ncols < 1) return PHB_EINVAL;
+  CK(cudaSetDevice(c->device));
+  const size_t n = (size_t)nrows * ncols;
+  CK(c->planes.ensure(n + (n + 1) / 2));
+  float *d_in = c->planes.p;
+  int16_t *d_out = reinterpret_cast<int16_t *>(c->planes.p + n);
+  CK(cudaMemcpy(d_in, h_grid, n * 4, cudaMemcpyHostToDevice));
+  int rc = phb_nc_pack_device(c, d_in, (int64_t)n, spval, d_out, add_offset, scale_factor, missing_value, nullptr);
+  if (rc) return rc;
+  CK(cudaMemcpy(h_packed, d_out, n * 2, cudaMemcpyDeviceToHost));
+  return PHB_OK;
+}
+
+int phb_nc_unpack_host(phb_ctx *c, const int16_t *h_packed, int nrows, int ncols, float add_offset, float scale_factor,
+                       int16_t missing_value, double spval, float *h_grid) {
+  if (!c || !h_packed || !h_grid || nrows < 1 || ncols < 1) return PHB_EINVAL;
+  CK(cudaSetDevice(c->device));
+  const size_t n = (size_t)nrows * ncols;
+  CK(c->planes.ensure(n + (n + 1) / 2));
+  float *d_out = c->planes.p;
+  int16_t *d_in = reinterpret_cast<int16_t *>(c->planes.p + n);
+  CK(cudaMemcpy(d_in, h_packed, n * 2, cudaMemcpyHostToDevice));
+  int rc = phb_nc_unpack_device(c, d_in, (int64_t)n, add_offset, scale_factor, missing_value, spval, d_out, nullptr);
+  if (rc) return rc;
+  CK(cudaMemcpy(h_grid, d_out, n * 4, cudaMemcpyDeviceToHost));
+  return PHB_OK;
+}
+
 /* ---- MODEL Lee_Kd_LS8 / Lee_Secchi_LS8 (secchi.c) --------------------------------------------------- */
 
 int phb_lee_ls8_device(phb_ctx *c, int mode, const float *d_coastal, const float *d_blue, const float *d_green,

@@ -421,8 +421,60 @@ def make_refine():
           int((res["out_31_1_0"] != -9999.0).sum()))
 
 
+def nc_pack_cases():
+    """Grids for the int16 packing goldens (small: stored with their outputs). The order-dependent range of
+    compress_2d (nc.c:286-298) is what the cases are about; a 300 x 333 grid spans many 4096-cell chunks of the
+    device passes, with record minima placed deep inside it."""
+    rng = np.random.default_rng(5)
+    g = rng.uniform(-40, 0, (37, 29)).astype(np.float32)
+    g[rng.uniform(size=g.shape) < 0.3] = -9999.0
+    yield "random", g
+    d = np.sort(rng.uniform(-40, 5, (11, 13)).astype(np.float32).ravel())[::-1].reshape(11, 13).copy()
+    yield "decreasing", d          # every value lowers the minimum: the maximum stays FLT_MIN and the shorts wrap
+    yield "increasing", d.ravel()[::-1].reshape(11, 13).copy()
+    f = g.copy()
+    f[0, 0] = 100.0                # the first value is the largest: it never reaches the maximum
+    yield "first_is_max", f
+    yield "flat", np.full((5, 7), 3.25, dtype=np.float32)
+    yield "all_spval", np.full((4, 4), -9999.0, dtype=np.float32)
+    h = g.copy()
+    h[2, 3], h[4, 5], h[6, 7] = np.nan, np.inf, -np.inf
+    yield "nan_inf", h
+    p = rng.uniform(1e-3, 50, (9, 9)).astype(np.float32)
+    p[0, 0] = -9999.0
+    yield "positive", p
+    big = rng.uniform(-30, -1, (300, 333)).astype(np.float32)
+    big[rng.uniform(size=big.shape) < 0.4] = -9999.0
+    flat = big.ravel()
+    for k, v in ((5000, 7.0), (5001, -35.0), (40000, 9.0), (40001, -36.0), (40002, 8.5), (90000, -37.0), (99000, 12.0)):
+        flat[k] = v                # a maximum right before a new minimum, one that IS a new minimum's neighbour, a late record
+    flat[99899] = -50.0            # a record minimum in the last chunk that would otherwise be the ...
+    yield "many_chunks", big
+    dec = np.linspace(20.0, -20.0, 3 * 4096 + 77, dtype=np.float32).reshape(1, -1).copy()
+    dec[0, 6000] = 19.5            # the only value that does not lower the running minimum, two chunks in
+    yield "decreasing_many_chunks", dec
+
+
+def make_nc_pack():
+    """compress_2d / decompress_2d of the unmodified nc.c (oracle/ref_nc.c includes it where it lies)."""
+    build()
+    ref = Oracle("reference")
+    res = {}
+    for name, g in nc_pack_cases():
+        packed, off, sc, miss = ref.nc_pack(g, -9999.0)
+        res[f"{name}_grid"] = g
+        res[f"{name}_packed"] = packed
+        res[f"{name}_meta"] = np.array([off, sc], dtype=np.float32)
+        res[f"{name}_missing"] = np.array([miss], dtype=np.int16)
+        res[f"{name}_unpacked"] = ref.nc_unpack(packed, off, sc, miss, -9999.0)
+    np.savez_compressed(os.path.join(HERE, "nc_pack.npz"), **res)
+    print("nc_pack:", len(res) // 5, "cases;", {n: (float(res[f"{n}_meta"][0]), float(res[f"{n}_meta"][1])) for n, _ in nc_pack_cases()})
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "refine":
+    if len(sys.argv) > 1 and sys.argv[1] == "nc_pack":
+        make_nc_pack()
+    elif len(sys.argv) > 1 and sys.argv[1] == "refine":
         make_refine()
     elif len(sys.argv) > 1 and sys.argv[1] == "mined":
         make_mined()
@@ -445,3 +497,4 @@ if __name__ == "__main__":
         make_refine()
         make_mined()
         make_restarts()
+        make_nc_pack()
