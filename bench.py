@@ -217,8 +217,11 @@ def main():
         raise SystemExit("bench.py: no CUDA device; photic_b200 has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    cpu_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        os.environ.setdefault("GLOO_SOCKET_IFNAME", "lo")  # one node; the container's hostname may not resolve
+        cpu_group = dist.new_group(backend="gloo")  # host-side barriers around the one-process e2e leg (see below)
     inv = Inverter(local)
     spec = scene_spec(args)
     K, W = args.steps, args.warmup
@@ -299,10 +302,13 @@ def main():
     # ---- end to end through the host-buffer C-ABI call ------------------------------------------------
     # N = 1: phb_invert_host. N > 1: phb_invert_host_multi from ONE process (rank 0) over the N devices of the box --
     # the plugin's own multi-GPU entry point, what the samodel() shim calls -- while the other ranks wait.
+    # The waiting ranks must wait on the HOST (gloo): an NCCL barrier would leave a spinning kernel on their device, and
+    # rank 0's kernels on that device -- another process, another context -- would be time-sliced against it.
     e2e = None
     if not args.no_e2e:
         if world > 1:
-            dist.barrier()
+            torch.cuda.synchronize()
+            dist.barrier(group=cpu_group)
         if rank == 0:
             hp, hpr = {}, {}
             for b in need:
@@ -341,7 +347,7 @@ def main():
                    "api": "phb_invert_host (pinned host planes in, host planes out)" if world == 1 else
                           f"phb_invert_host_multi from one process over {world} devices (pinned host planes in, host planes out)"}
         if world > 1:
-            dist.barrier()
+            dist.barrier(group=cpu_group)
 
     if rank == 0:
         alg_flops, ms_solve = float(agg[0]), float(agg[1]) / world
