@@ -112,6 +112,8 @@ def lib() -> C.CDLL:
         L.phb_kat_objective.argtypes = [C.c_void_p, C.POINTER(SceneDesc), C.c_int, C.c_int, C.c_int, _dp, C.c_int,
                                         C.c_int, _dp, _dp]
         L.phb_kat_math.argtypes = [C.c_void_p, C.c_int, _dp, _dp, C.c_int64, _dp]
+        L.phb_eval_bench.argtypes = [C.c_void_p, C.POINTER(SceneDesc), C.c_int, C.c_int, C.c_int, _dp, C.c_int, _dp,
+                                     C.c_int, C.c_int, C.c_int, _dp, _dp, _fp]
         L.phb_refine_minmax_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_float, _fp, C.c_void_p]
         L.phb_refine_device.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_float, C.c_void_p,
                                         C.c_float, C.c_int64, C.c_int, _fp, _fp, C.c_void_p, C.c_void_p]
@@ -163,7 +165,7 @@ PHB_OK, PHB_EINVAL, PHB_ENODEVICE, PHB_ECUDA, PHB_ENOMEM, PHB_ENOFIT, PHB_ENOPEE
 
 EXPORTS = ["phb_version", "phb_error_string", "phb_device_count", "phb_ctx_create", "phb_ctx_destroy",
            "phb_band_tables", "phb_invert_device", "phb_invert_host", "phb_debug_record_len", "phb_invert_host_debug",
-           "phb_kat_objective", "phb_kat_math", "phb_refine_minmax_device", "phb_refine_device", "phb_refine_host",
+           "phb_kat_objective", "phb_kat_math", "phb_eval_bench", "phb_refine_minmax_device", "phb_refine_device", "phb_refine_host",
            "phb_fp64_peak", "phb_depth_sigma_host", "phb_lee_ls8_device", "phb_lee_ls8_host",
            "phb_jerlov_fit", "phb_jerlov_k", "phb_jerlov_k_from_ratio",
            "phb_plan_row_bands", "phb_invert_host_multi", "phb_debug_model_const", "phb_invert_rows",

@@ -46,6 +46,209 @@ __global__ void kat_objective_kernel(const SolveParams p, int nb_active, int n_r
   }
 }
 
+/* ---- mapping study: the objective by a TEAM of warps, and a closed-loop evaluation benchmark -------------------
+ * north_star asks that the pixel-to-thread mapping be chosen on ncu evidence. The product maps one pixel to one warp
+ * (objective()). The alternative -- a pixel on TW co-operating warps ("CTA per pixel" for TW = 16) -- is built here for
+ * the part of the work that can be spread at all, the forward-model terms: the (scene,band) and (region,substrate)
+ * pre-passes go to different warps, the Nr * SB terms are dealt over 32 * TW lanes, and then ONE warp adds the squared
+ * residuals in the reference's order (a sum that cannot be split without changing its bits) and runs the penalties,
+ * while the others wait at the team's named barrier. Same operations on the same operands as objective(): the results
+ * are bit-identical (tests/test_gpu_parity.py::test_team_objective_equals_warp_objective). eval_bench_kernel runs either
+ * form in a closed loop (the next vector depends on the last value, as in the simplex), 16 warps per SM, so the two
+ * mappings can be timed and profiled on equal terms (tests/manual/mapping_study.py). */
+__device__ __forceinline__ void team_sync(int bar_id, int n_threads) {
+#ifndef PHB_HOST_EMU
+  asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(n_threads) : "memory");
+#endif
+}
+
+template <int NB, int SBP, int TW>
+__device__ __forceinline__ double objective_team(const Warp &w, const Pixel &px, int lane, int wt, int bar_id, int SB, int Ns,
+                                                 int NbMaxRt, const double *__restrict__ x, Side &side, double *xchg) {
+  const int Nr = px.Nr, T = px.T, off = px.off;
+  const int Nb = NB > 0 ? NB : px.Nb;
+  const int NbS = NB > 0 ? NB : NbMaxRt;
+  constexpr CtaOff CO = cta_offsets(SBP);
+  constexpr WarpOff WO = warp_offsets(SBP);
+  const uint64_t *const c_exp = reinterpret_cast<const uint64_t *>(phb_smem + CO.exp);
+  const double *const c_bbw = reinterpret_cast<const double *>(phb_smem + CO.bbw);
+  const double *const c_secs = reinterpret_cast<const double *>(phb_smem + CO.secs);
+  const double *const c_secv = reinterpret_cast<const double *>(phb_smem + CO.secv);
+  const double *const c_a0 = reinterpret_cast<const double *>(phb_smem + CO.a0);
+  const double *const c_a1 = reinterpret_cast<const double *>(phb_smem + CO.a1);
+  const double *const c_aw = reinterpret_cast<const double *>(phb_smem + CO.aw);
+  const double *const c_agexp = reinterpret_cast<const double *>(phb_smem + CO.agexp);
+  const double *const c_bot = reinterpret_cast<const double *>(phb_smem + CO.bot);
+  const int *const c_sof = reinterpret_cast<const int *>(phb_smem + CO.sof);
+  unsigned char *const wblk = phb_smem + w.wofs;
+  double *const a_sb = reinterpret_cast<double *>(wblk + WO.a);
+  double *const X_sb = reinterpret_cast<double *>(wblk + WO.X);
+  double *const K_sb = reinterpret_cast<double *>(wblk + WO.K);
+  double *const qB = reinterpret_cast<double *>(wblk + WO.qB);
+  constexpr int TL = 32 * TW; /* lanes of the team */
+
+  /* pre-passes (objective(): samodel.c:2889-2893 and 2482-2496), one warp each */
+  if (wt == 0) {
+#pragma unroll 1
+    for (int sb = lane; sb < SB; sb += 32) {
+      const int s = c_sof[sb];
+      const double P = 0.01 * fabs(x[off + 3 * s]);
+      const double G = 0.01 * fabs(x[off + 1 + 3 * s]);
+      const double a_phi = (c_a0[sb] + c_a1[sb] * phm::log(P, w.log_tab)) * P;
+      const double a_g = G * c_agexp[sb];
+      a_sb[sb] = c_aw[sb] + a_phi + a_g;
+      X_sb[sb] = 0.01 * fabs(x[off + 2 + 3 * s]);
+    }
+  }
+  if (wt == (TW > 1 ? 1 : 0)) {
+#pragma unroll 1
+    for (int idx = lane; idx < Nr * NbS; idx += 32) {
+      const int r = idx / NbS, k = idx - r * NbS;
+      double qb = 0.0;
+      if (k < Nb) {
+        const double *xq = x + Nr + Nr * Nb + r * Nb;
+        double q_sum = fabs(xq[0]);
+#pragma unroll 1
+        for (int kk = 1; kk < Nb; kk++) q_sum += fabs(xq[kk]);
+        const double xb = fabs(x[Nr + r * Nb + k]), q = fabs(xq[k]);
+        const double xbq = xb * q;
+        if (in_fast_range(q_sum) && in_fast_range(q) && in_fast_range(xbq)) {
+          const double rs = rcp_refined(q_sum);
+          const double q1 = __dmul_rn(q, rs), q2 = __dmul_rn(xbq, rs);
+          qb = __fma_rn(rs, __fma_rn(-q_sum, q1, q), q1) * (0.01 * xb);
+          w.bq[r * Nb + k] = __fma_rn(rs, __fma_rn(-q_sum, q2, xbq), q2);
+        } else {
+          qb = div_rn(q, q_sum) * (0.01 * xb);
+          w.bq[r * Nb + k] = div_rn(xbq, q_sum);
+        }
+      }
+      qB[idx] = qb;
+    }
+  }
+  team_sync(bar_id, TL);
+
+  /* forward-model terms (samodel.c:2911-2944), term t on team lane t mod TL; no sum here */
+  const int Tpad = (T + 31) & ~31;
+  {
+    const int tl = wt * 32 + lane;
+    int r = tl / SB, sb = tl - r * SB;
+    const int step_r = TL / SB, step_sb = TL - step_r * SB;
+#pragma unroll 1
+    for (int t0 = wt * 32; t0 < T; t0 += TL) { /* warp-uniform: a round whose 32 terms are all past the last is skipped */
+      const int t = t0 + lane;
+      const bool live = t < T;
+      const double H = fabs(x[r]);
+      const double *qb = qB + r * NbS;
+      double rho = qb[0] * c_bot[sb];
+      if (NB > 0) {
+#pragma unroll
+        for (int kb = 1; kb < NB; kb++) rho += qb[kb] * c_bot[kb * SBP + sb];
+      } else {
+#pragma unroll 1
+        for (int kb = 1; kb < NbS; kb++) rho += qb[kb] * c_bot[kb * SBP + sb];
+      }
+      const double a = a_sb[sb];
+      const double bb = c_bbw[sb] + X_sb[sb] * w.powY[t];
+      const double secs = c_secs[sb], secv = c_secv[sb];
+      const double apb = a + bb;
+      bool ok = in_fast_range(bb) && in_fast_range(apb);
+      const double u = fast_div(bb, apb);
+      double K = apb;
+      if (K < 0.0) K = 0.0;
+      if (K > 2.5) K = 2.5;
+      const double rrs_dp = (kHot[H_084] + kHot[H_170] * u) * u;
+      const double DuC = kHot[H_103] * fast_sqrt(1.0 + kHot[H_24] * u);
+      const double DuB = kHot[H_104] * fast_sqrt(1.0 + kHot[H_54] * u);
+      ok = ok && unit_range(u);
+      const double M1 = secs + DuC * secv;
+      const double x1 = -M1 * K * H;
+      const double M2 = secs + DuB * secv;
+      const double x2 = -M2 * K * H;
+      ok = ok && exp_arg_in_main_range(x1) && exp_arg_in_main_range(x2);
+      const double rrs_C = rrs_dp * (1.0 - exp_main_c(x1, c_exp));
+      ok = ok && in_fast_range(rho);
+      const double rrs_B = div_by_pi(rho) * exp_main_c(x2, c_exp);
+      const double rrs = rrs_C + rrs_B;
+      const double num = 0.5 * rrs, den = 1.0 - 1.5 * rrs;
+      ok = ok && in_fast_range(num) && in_fast_range(den);
+      double Rrs = fast_div(num, den);
+      if (!ok && live) Rrs = term_reference<false>(H, rho, a, bb, secs, secv, c_exp);
+      const double d = Rrs - w.meas[t];
+      w.d2[kD2Zeros + t] = live ? d * d : 0.0; /* t < Tpad: the tables and d2 are padded to whole rounds of 32 */
+      if (r == Nr - 1) K_sb[sb] = K;
+      r += step_r; sb += step_sb;
+      if (sb >= SB) { sb -= SB; r += 1; }
+    }
+  }
+  team_sync(bar_id, TL);
+
+  /* the ordered sum and everything after it: one warp (the others wait below) */
+  if (wt == 0) {
+    double err = 0.0;
+    const double2 *dv = reinterpret_cast<const double2 *>(w.d2 + kD2Zeros);
+#pragma unroll 1
+    for (int q = 0; q < Tpad; q += 8, dv += 4) {
+      const double2 v0 = dv[0], v1 = dv[1], v2 = dv[2], v3 = dv[3];
+      err += v0.x; err += v0.y; err += v1.x; err += v1.y; err += v2.x; err += v2.y; err += v3.x; err += v3.y;
+    }
+    const double e = objective_tail<NB, SBP, false>(w, px, lane, Ns, NbMaxRt, x, err, side);
+    if (lane == 0) *xchg = e;
+  }
+  team_sync(bar_id, TL);
+  return *xchg;
+}
+
+/* Closed-loop evaluation benchmark: every team (TW = 1: every warp, with the product's objective()) holds one pixel and
+ * evaluates the objective `reps` times, each vector derived from the last value. out[2 * team] = sum of the values,
+ * out[2 * team + 1] = the first value (checked against the known answers). */
+template <int NB, int SBP, int TW>
+__global__ void __launch_bounds__(kMaxThreads, 1)
+eval_bench_kernel(const SolveParams p, int n_regions, int origin, const double *meas, const double *params, int reps,
+                  int same_smsp, double *out) {
+  const ModelConst &M = *p.M;
+  stage_cta(p, M, phb_smem);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5, n_teams = W / TW;
+  /* same_smsp: the warps of a team are warp, warp + n_teams, ...: the same scheduler (warp mod 4) when n_teams is a
+   * multiple of 4; otherwise consecutive warps, one per scheduler */
+  const int team = same_smsp ? warp % n_teams : warp / TW, wt = same_smsp ? warp / n_teams : warp % TW;
+  const int bar_id = 1 + team, SB = p.L.SB, Ns = p.L.Ns;
+  Warp w;
+  bind_warp(w, p, p.L, phb_smem, team, blockIdx.x * n_teams + team);
+  Pixel px;
+  px.Nr = n_regions; px.Nb = NB; px.origin = origin;
+  size_pixel(px, lane, SB, Ns, p.L.simplex_doubles, 0);
+  px.mean_meas = 0.0;
+  double *xchg = w.rcp + 7;
+  if (wt == 0) {
+    for (int t = lane; t < px.T; t += 32) w.meas[t] = meas[t];
+    for (int t = px.T + lane; t < ((px.T + 31) & ~31); t += 32) { w.meas[t] = 0.0; w.powY[t] = 0.0; }
+    __syncwarp();
+    phm::Tables tb;
+    tb.exp_tab = w.exp_tab; tb.log_tab = p.log_tab; tb.pow_tab = p.pow_tab;
+    double Bs, Ps, Xs;
+    derive_pixel_constants(w, px, M, tb, lane, SB, Ns, Bs, Ps, Xs);
+    for (int i = lane; i < px.n; i += 32) w.xmin[i] = params[i];
+    __syncwarp();
+  }
+  if (TW > 1) team_sync(bar_id, 32 * TW);
+  const double x0 = params[0];
+  Side side;
+  double acc = 0.0, first = 0.0;
+#pragma unroll 1
+  for (int rep = 0; rep < reps; rep++) {
+    double e;
+    if (TW == 1) e = objective<NB, SBP, false>(w, px, lane, SB, Ns, p.L.NbMax, w.xmin, side);
+    else e = objective_team<NB, SBP, TW>(w, px, lane, wt, bar_id, SB, Ns, p.L.NbMax, w.xmin, side, xchg);
+    if (rep == 0) first = e;
+    acc += e;
+    /* the next vector depends on this value (as the simplex's next vertex does): depth of region 0 nudged */
+    if (wt == 0 && lane == 0) w.xmin[0] = x0 * (1.0 + 1.0e-6 * (double)((rep & 7) + 1)) + 1.0e-9 * e;
+    if (TW > 1) team_sync(bar_id, 32 * TW); else __syncwarp();
+  }
+  if (wt == 0 && lane == 0) { out[2 * (blockIdx.x * n_teams + team)] = acc; out[2 * (blockIdx.x * n_teams + team) + 1] = first; }
+}
+
 /* ---- known answers: the exact libm port --------------------------------------------------------- */
 __global__ void kat_math_kernel(int fn, const double *x, const double *y, long long n, double *out,
                                 const unsigned long long *exp_tab, const double *log_tab, const double *pow_tab) {
@@ -304,7 +507,17 @@ __global__ void nc_unpack_kernel(const short *in, long long n, float add_offset,
                                  float fspv, float *out) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const short c = in[i];
-    out[i] = (c == missing) ? fspv : __fadd_rn(__fmul_rn((float)c, scale_factor), add_offset); /* nc.c:259-262 */
+    float r = fspv;
+    if (c != missing) { /* nc.c:259-262 */
+      /* NaN results carry x86's bits: an invalid operation (0 * inf, inf - inf: a grid that held infinities has an
+       * infinite range) gives the "real indefinite" 0xffc00000, a NaN operand is passed on quieted -- the device's
+       * own NaN is 0x7fffffff */
+      float t = __fmul_rn((float)c, scale_factor);
+      if (t != t) t = (scale_factor != scale_factor) ? __uint_as_float(__float_as_uint(scale_factor) | 0x00400000u) : __uint_as_float(0xffc00000u);
+      r = __fadd_rn(t, add_offset);
+      if (r != r) r = (t != t) ? t : (add_offset != add_offset) ? __uint_as_float(__float_as_uint(add_offset) | 0x00400000u) : __uint_as_float(0xffc00000u);
+    }
+    out[i] = r;
   }
 }
 

@@ -361,6 +361,22 @@ int phb_debug_record_len(const phb_scene_desc *d) {
 
 struct LaunchGeom { int W, ctas, smem, regs; };
 
+/* the most simplex rows any pixel of a class leaves in the global slab (size_pixel() of invert_kernel.cuh, over every
+ * neighbourhood size): the slabs are that deep, so all of them together are small enough to stay in L2 */
+static int max_global_rows(const SmemLayout &L, int NrMax, int Ns, int nb) {
+  int most = 0;
+  for (int Nr = 1; Nr <= NrMax; Nr++) {
+    const int n = Nr + 2 * Nr * nb + 3 * Ns, KB = (n + 31) >> 5;
+    int jT = (PHB_USE_TMEM && KB <= 3) ? L.tmem_cols / (2 * KB) : 0;
+    if (jT > n + 1) jT = n + 1;
+    int jS = L.simplex_doubles / n;
+    if (jT + jS > n + 1) jS = n + 1 - jT;
+    const int jG = n + 1 - jT - jS;
+    if (jG > most) most = jG;
+  }
+  return most;
+}
+
 /* Shared-memory layout, launch geometry and launch of the persistent solve kernel (pixel queues or, trials = true,
  * chains of depth-error trials). sp arrives with the work description filled in (views, classes, trial arrays); the
  * model, layouts, slabs, counters and libm tables are bound here. */
@@ -369,7 +385,6 @@ static int launch_solve(phb_ctx *c, const ModelConst &M, SolveParams &sp, bool t
   const int NrMax = (2 * nsp - 1) * (2 * nsp - 1);
   sp.L = make_layout(M.SB, M.n_scenes, M.n_bottoms, NrMax);
   const long long simplex_doubles = (long long)(sp.L.nmax + 1) * sp.L.nmax;
-  const long long slab_doubles = simplex_doubles + sp.L.nmax + sp.L.Tmax + (long long)((sp.L.nmax + 8) / 8 + 1) * sp.L.nmax; /* + centroid checkpoints */
   /* kernel instantiation: compile-time substrate count for the default NBOTTOMS 3 (followed, with two pixel classes,
    * by the one-substrate code for the sand-only queue), run-time loop otherwise; compile-time (scene,band) stride 32
    * (up to 8 dates x 4 bands) or the maximum */
@@ -416,12 +431,22 @@ static int launch_solve(phb_ctx *c, const ModelConst &M, SolveParams &sp, bool t
   int ctas = c->n_sm;
   if (const char *e = getenv("PHB_CTAS")) { int v = atoi(e); if (v >= 1) ctas = v; }
   const size_t smem = (size_t)sp.L.cta_bytes + (size_t)W * sp.L.warp_bytes;
+  /* slab depth: the global-tier rows of the deepest simplex of either class (at least one row: nothing is ever empty) */
+  int slab_rows = max_global_rows(sp.L, NrMax, M.n_scenes, M.n_bottoms);
+  { const int r1 = max_global_rows(sp.L, NrMax, M.n_scenes, 1); if (r1 > slab_rows) slab_rows = r1; }
+  if (sp.n_classes > 1) { const int r1 = max_global_rows(sp.L1, NrMax, M.n_scenes, 1); if (r1 > slab_rows) slab_rows = r1; }
+  if (slab_rows < 1) slab_rows = 1;
+  const long long slab_doubles = (((long long)slab_rows * sp.L.nmax + sp.L.nmax + sp.L.Tmax +
+                                   (long long)((sp.L.nmax + 8) / 8 + 1) * sp.L.nmax /* centroid checkpoints */) + 15) & ~15LL;
   CK(c->slabs.ensure((size_t)ctas * W * slab_doubles));
   sp.M = c->d_model;
-  sp.slabs = c->slabs.p; sp.slab_stride = slab_doubles;
+  sp.slabs = c->slabs.p; sp.slab_stride = slab_doubles; sp.slab_rows = slab_rows;
   sp.counters = c->d_counters; sp.flops = c->d_flops;
   sp.exp_tab = c->d_exp_tab; sp.log_tab = c->d_log_tab; sp.pow_tab = c->d_pow_tab;
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  /* (A persisting-L2 access-policy window over the slabs was tried in round 2 and removed: DRAM write-back went UP 2.4x
+   * -- the carve-out takes capacity from everything else and only a random share of the window's lines is kept -- with
+   * no change in throughput. What reaches DRAM is one write-back per line stored into the global tier, ~13 GB/s.) */
   kern<<<ctas, W * 32, smem, st>>>(sp);
   {
     cudaError_t le = cudaGetLastError();
@@ -1501,6 +1526,79 @@ int phb_kat_objective(phb_ctx *c, const phb_scene_desc *desc, int nb_active, int
   CK(cudaGetLastError());
   CK(cudaMemcpy(out6, d_out, (size_t)nvec * 6 * 8, cudaMemcpyDeviceToHost));
   cudaFree(d_meas); cudaFree(d_par); cudaFree(d_out);
+  return PHB_OK;
+}
+
+/* Mapping study (aux_kernels.cuh:eval_bench_kernel): closed-loop objective evaluations on every SM, 16 warps per SM,
+ * one pixel per team of `team_warps` warps (1: the product's warp-per-pixel objective()). */
+int phb_eval_bench(phb_ctx *c, const phb_scene_desc *desc, int nb_active, int n_regions, int origin,
+                   const double *rrs_measured, int nparams, const double *params, int team_warps, int same_smsp, int reps,
+                   double *first_value, double *evals_per_s, float *ms_out) {
+  if (!c || !rrs_measured || !params || reps < 1) return PHB_EINVAL;
+  if (nb_active != 1 && nb_active != 3) return PHB_EINVAL;
+  if (team_warps != 1 && team_warps != 2 && team_warps != 4 && team_warps != 8) return PHB_EINVAL;
+  int rc = validate(desc);
+  if (rc) return rc;
+  CK(cudaSetDevice(c->device));
+  ModelConst M;
+  phb_scene_desc dd = *desc;
+  dd.n_bottoms = nb_active;
+  build_model(&dd, &M);
+  if (M.SB > 32 || n_regions < 1 || n_regions > 16) return PHB_EINVAL; /* the compile-time classes of the product */
+  CK(cudaMemcpy(c->d_model, &M, sizeof(M), cudaMemcpyHostToDevice));
+  SolveParams sp;
+  memset(&sp, 0, sizeof(sp));
+  sp.L = make_layout(M.SB, M.n_scenes, nb_active, n_regions);
+  if (nparams != sp.L.nmax) return PHB_EINVAL;
+  sp.M = c->d_model;
+  sp.exp_tab = c->d_exp_tab; sp.log_tab = c->d_log_tab; sp.pow_tab = c->d_pow_tab;
+  const int W = 16, ctas = c->n_sm, n_teams = ctas * (W / team_warps);
+  const size_t nm = (size_t)n_regions * M.SB;
+  std::vector<double> flat(nm);
+  for (int r = 0; r < n_regions; r++)
+    for (int s = 0; s < M.n_scenes; s++)
+      for (int b = 0; b < M.n_bands[s]; b++)
+        flat[(size_t)r * M.SB + M.sb_begin[s] + b] = rrs_measured[((size_t)r * M.n_scenes + s) * M.max_bands + b];
+  struct Scratch { /* released on every return path */
+    DevBuf<double> meas, par, out;
+    ~Scratch() { meas.release(); par.release(); out.release(); }
+  } scratch;
+  DevBuf<double> &d_meas = scratch.meas, &d_par = scratch.par, &d_out = scratch.out;
+  CK(d_meas.ensure(nm)); CK(d_par.ensure(nparams)); CK(d_out.ensure((size_t)2 * n_teams));
+  CK(cudaMemcpy(d_meas.p, flat.data(), nm * 8, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_par.p, params, (size_t)nparams * 8, cudaMemcpyHostToDevice));
+  /* the product's shared-memory footprint (one CTA per SM either way) */
+  const size_t smem = (size_t)sp.L.cta_bytes + (size_t)W * sp.L.warp_bytes;
+  if (smem > c->smem_optin) return PHB_EINVAL;
+  typedef void (*bench_fn)(const SolveParams, int, int, const double *, const double *, int, int, double *);
+  bench_fn kk = nullptr;
+#define PHB_PICK(NB_) \
+  (team_warps == 1 ? (bench_fn)eval_bench_kernel<NB_, 32, 1> : team_warps == 2 ? (bench_fn)eval_bench_kernel<NB_, 32, 2> : \
+   team_warps == 4 ? (bench_fn)eval_bench_kernel<NB_, 32, 4> : (bench_fn)eval_bench_kernel<NB_, 32, 8>)
+  kk = nb_active == 3 ? PHB_PICK(3) : PHB_PICK(1);
+#undef PHB_PICK
+  CK(cudaFuncSetAttribute(kk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  CK(cudaEventRecord(e0, 0));
+  kk<<<ctas, W * 32, smem>>>(sp, n_regions, origin, d_meas.p, d_par.p, reps, same_smsp ? 1 : 0, d_out.p);
+  cudaError_t le = cudaGetLastError();
+  CK(cudaEventRecord(e1, 0));
+  cudaError_t se = cudaEventSynchronize(e1);
+  float ms = 0.0f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  if (le != cudaSuccess) { g_last_cuda_error = std::string("eval_bench_kernel: ") + cudaGetErrorString(le); return PHB_ECUDA; }
+  if (se != cudaSuccess) { g_last_cuda_error = std::string("eval_bench_kernel: ") + cudaGetErrorString(se); return PHB_ECUDA; }
+  std::vector<double> out((size_t)2 * n_teams);
+  CK(cudaMemcpy(out.data(), d_out.p, out.size() * 8, cudaMemcpyDeviceToHost));
+  if (first_value) {
+    *first_value = out[1];
+    for (int t = 1; t < n_teams; t++) /* every team evaluated the same vector: any difference is a bug */
+      if (memcmp(&out[2 * t + 1], &out[1], 8) != 0) return PHB_EINVAL;
+  }
+  if (ms_out) *ms_out = ms;
+  if (evals_per_s) *evals_per_s = (double)n_teams * reps / (ms * 1e-3);
   return PHB_OK;
 }
 

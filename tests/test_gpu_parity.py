@@ -243,6 +243,29 @@ def test_objective_extreme_parameters_take_the_fallback_paths(inverter, generic,
         assert eq.all(), (tag, np.argwhere(~eq)[:8], got[~eq][:8], k[f"{tag}_out"][~eq][:8])
 
 
+def test_team_objective_equals_warp_objective(inverter):
+    """Mapping study (aux_kernels.cuh): the objective evaluated by a team of 2 / 4 / 8 warps -- terms dealt over the
+    team's lanes, ordered sum and penalties on one warp -- gives the bits of the one-warp objective, which are the
+    reference's (golden), in both warp-to-scheduler placements and on every SM."""
+    from photic_b200 import capi, scene
+    k = load_golden("kat_objective")
+    seen = 0
+    for tag in "abcd":
+        ns, nb, nr, origin = (int(v) for v in k[f"{tag}_meta"])
+        if nb not in (1, 3) or nr > 16 or ns * 4 > 32:
+            continue
+        spec = replace(scene.CONFIGS["murion"], n_dates=ns)
+        desc = capi.desc_from_spec(spec)
+        for v in (0, 1, 7):
+            want = k[f"{tag}_out"][v, 0]
+            for tw in (1, 2, 4, 8):
+                for same in (False, True):
+                    got, rate, ms = inverter.eval_bench(desc, nb, nr, origin, k[f"{tag}_meas"], k[f"{tag}_params"][v], tw, same, reps=3)
+                    assert np.float64(got).view(np.int64) == np.float64(want).view(np.int64), (tag, v, tw, same, got, want)
+                    seen += 1
+    assert seen >= 48
+
+
 def test_device_math_equals_host_libm(inverter):
     """exp/log/pow on the device == the libm the reference links (same process, math module / numpy ufunc free)."""
     import math
