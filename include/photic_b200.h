@@ -256,11 +256,12 @@ int phb_kat_objective(phb_ctx *ctx, const phb_scene_desc *desc, int n_bottoms_ac
 /* Mapping study: closed-loop objective evaluations on every SM, 16 warps per SM, one pixel per
  * team of `team_warps` warps -- 1 is the product's mapping (one warp per pixel), 2 / 4 / 8 spread the forward-model terms
  * of one pixel over that many warps and leave the ordered sum and the penalties to one of them. same_smsp != 0 puts the
- * warps of a team on one scheduler. Returns the value of the first evaluation (bit-identical between mappings), the
- * rate and the kernel time. */
+ * warps of a team on one scheduler; skew_cycles > 0 starts team t of an SM t * skew_cycles late, so that the teams stay
+ * out of phase as the warps of the solve kernel are (0: in step). Returns the value of the first evaluation
+ * (bit-identical between mappings), the rate and the kernel time. */
 int phb_eval_bench(phb_ctx *ctx, const phb_scene_desc *desc, int n_bottoms_active, int n_regions, int origin,
-                   const double *rrs_measured, int nparams, const double *params, int team_warps, int same_smsp, int reps,
-                   double *first_value, double *evals_per_s, float *ms);
+                   const double *rrs_measured, int nparams, const double *params, int team_warps, int same_smsp,
+                   int skew_cycles, int reps, double *first_value, double *evals_per_s, float *ms);
 int phb_kat_math(phb_ctx *ctx, int fn /*0 exp,1 log,2 pow,3 fast_div,4 fast_sqrt,5 a/b,6 sqrt,7 exp_main,8 x/pi fast,9-11 range predicates,12 log10,13/15 guarded a/b,14 guarded sqrt*/, const double *x,
                  const double *y, int64_t n, double *out);
 

@@ -113,7 +113,7 @@ def lib() -> C.CDLL:
                                         C.c_int, _dp, _dp]
         L.phb_kat_math.argtypes = [C.c_void_p, C.c_int, _dp, _dp, C.c_int64, _dp]
         L.phb_eval_bench.argtypes = [C.c_void_p, C.POINTER(SceneDesc), C.c_int, C.c_int, C.c_int, _dp, C.c_int, _dp,
-                                     C.c_int, C.c_int, C.c_int, _dp, _dp, _fp]
+                                     C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp, _fp]
         L.phb_refine_minmax_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_float, _fp, C.c_void_p]
         L.phb_refine_device.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_float, C.c_void_p,
                                         C.c_float, C.c_int64, C.c_int, _fp, _fp, C.c_void_p, C.c_void_p]

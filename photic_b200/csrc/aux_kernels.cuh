@@ -204,7 +204,7 @@ __device__ __forceinline__ double objective_team(const Warp &w, const Pixel &px,
 template <int NB, int SBP, int TW>
 __global__ void __launch_bounds__(kMaxThreads, 1)
 eval_bench_kernel(const SolveParams p, int n_regions, int origin, const double *meas, const double *params, int reps,
-                  int same_smsp, double *out) {
+                  int same_smsp, int skew_cycles, double *out) {
   const ModelConst &M = *p.M;
   stage_cta(p, M, phb_smem);
   __syncthreads();
@@ -232,6 +232,14 @@ eval_bench_kernel(const SolveParams p, int n_regions, int origin, const double *
     __syncwarp();
   }
   if (TW > 1) team_sync(bar_id, 32 * TW);
+  /* skew_cycles > 0: team t starts t * skew_cycles late, so the teams of an SM -- which all run the same code at the same
+   * speed -- stay out of phase for the whole run, as the warps of the solve kernel are (different pixels, different
+   * evaluation counts); 0: they run in step */
+  if (skew_cycles > 0) {
+    const long long t0 = clock64(), wait = (long long)team * skew_cycles;
+    while (clock64() - t0 < wait) {}
+    if (TW > 1) team_sync(bar_id, 32 * TW); else __syncwarp();
+  }
   const double x0 = params[0];
   Side side;
   double acc = 0.0, first = 0.0;

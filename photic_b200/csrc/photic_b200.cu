@@ -441,6 +441,7 @@ static int launch_solve(phb_ctx *c, const ModelConst &M, SolveParams &sp, bool t
   CK(c->slabs.ensure((size_t)ctas * W * slab_doubles));
   sp.M = c->d_model;
   sp.slabs = c->slabs.p; sp.slab_stride = slab_doubles; sp.slab_rows = slab_rows;
+  if (const char *e = getenv("PHB_ALIGN")) sp.align_evals = atoi(e) != 0 ? 1 : 0;
   sp.counters = c->d_counters; sp.flops = c->d_flops;
   sp.exp_tab = c->d_exp_tab; sp.log_tab = c->d_log_tab; sp.pow_tab = c->d_pow_tab;
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1532,9 +1533,9 @@ int phb_kat_objective(phb_ctx *c, const phb_scene_desc *desc, int nb_active, int
 /* Mapping study (aux_kernels.cuh:eval_bench_kernel): closed-loop objective evaluations on every SM, 16 warps per SM,
  * one pixel per team of `team_warps` warps (1: the product's warp-per-pixel objective()). */
 int phb_eval_bench(phb_ctx *c, const phb_scene_desc *desc, int nb_active, int n_regions, int origin,
-                   const double *rrs_measured, int nparams, const double *params, int team_warps, int same_smsp, int reps,
-                   double *first_value, double *evals_per_s, float *ms_out) {
-  if (!c || !rrs_measured || !params || reps < 1) return PHB_EINVAL;
+                   const double *rrs_measured, int nparams, const double *params, int team_warps, int same_smsp,
+                   int skew_cycles, int reps, double *first_value, double *evals_per_s, float *ms_out) {
+  if (!c || !rrs_measured || !params || reps < 1 || skew_cycles < 0) return PHB_EINVAL;
   if (nb_active != 1 && nb_active != 3) return PHB_EINVAL;
   if (team_warps != 1 && team_warps != 2 && team_warps != 4 && team_warps != 8) return PHB_EINVAL;
   int rc = validate(desc);
@@ -1570,7 +1571,7 @@ int phb_eval_bench(phb_ctx *c, const phb_scene_desc *desc, int nb_active, int n_
   /* the product's shared-memory footprint (one CTA per SM either way) */
   const size_t smem = (size_t)sp.L.cta_bytes + (size_t)W * sp.L.warp_bytes;
   if (smem > c->smem_optin) return PHB_EINVAL;
-  typedef void (*bench_fn)(const SolveParams, int, int, const double *, const double *, int, int, double *);
+  typedef void (*bench_fn)(const SolveParams, int, int, const double *, const double *, int, int, int, double *);
   bench_fn kk = nullptr;
 #define PHB_PICK(NB_) \
   (team_warps == 1 ? (bench_fn)eval_bench_kernel<NB_, 32, 1> : team_warps == 2 ? (bench_fn)eval_bench_kernel<NB_, 32, 2> : \
@@ -1581,7 +1582,7 @@ int phb_eval_bench(phb_ctx *c, const phb_scene_desc *desc, int nb_active, int n_
   cudaEvent_t e0, e1;
   CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
   CK(cudaEventRecord(e0, 0));
-  kk<<<ctas, W * 32, smem>>>(sp, n_regions, origin, d_meas.p, d_par.p, reps, same_smsp ? 1 : 0, d_out.p);
+  kk<<<ctas, W * 32, smem>>>(sp, n_regions, origin, d_meas.p, d_par.p, reps, same_smsp ? 1 : 0, skew_cycles, d_out.p);
   cudaError_t le = cudaGetLastError();
   CK(cudaEventRecord(e1, 0));
   cudaError_t se = cudaEventSynchronize(e1);

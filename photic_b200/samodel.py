@@ -202,14 +202,16 @@ class Inverter:
                                          npar, nvec, _np_ptr(params, capi._dp), _np_ptr(out, capi._dp)))
         return out
 
-    def eval_bench(self, desc: SceneDesc, nb_active, n_regions, origin, meas, params, team_warps=1, same_smsp=False, reps=1):
+    def eval_bench(self, desc: SceneDesc, nb_active, n_regions, origin, meas, params, team_warps=1, same_smsp=False, reps=1,
+                   skew_cycles=0):
         """Mapping study (phb_eval_bench): closed-loop objective evaluations on every SM with one pixel per team of
         `team_warps` warps (1 = the product's warp-per-pixel objective). Returns (first value, evaluations/s, ms)."""
         meas = np.ascontiguousarray(meas, dtype=np.float64)
         params = np.ascontiguousarray(params, dtype=np.float64).reshape(-1)
         first, rate, ms = C.c_double(0.0), C.c_double(0.0), C.c_float(0.0)
         check(self.lib.phb_eval_bench(self.ctx, C.byref(desc), nb_active, n_regions, origin, _np_ptr(meas, capi._dp),
-                                      params.size, _np_ptr(params, capi._dp), team_warps, 1 if same_smsp else 0, reps,
+                                      params.size, _np_ptr(params, capi._dp), team_warps, 1 if same_smsp else 0,
+                                      int(skew_cycles), reps,
                                       C.byref(first), C.byref(rate), C.byref(ms)))
         return first.value, rate.value, ms.value
 

@@ -120,15 +120,22 @@ def row_cost(valid: torch.Tensor, shallow: torch.Tensor, shallow_weight: float =
 # tools/class_cost.py). Normalised to the 8-12 m sand-only bin.
 _COST_EDGES = (2.0, 4.0, 6.0, 8.0, 12.0, 16.0, 24.0, 32.0)
 _COST_WEIGHT = (2.4, 2.9, 2.6, 2.2, 1.0, 1.1, 1.05, 1.35, 1.4)
+_COST_NO_PRIOR = 8.0 * 2.4  # eight H starts, all substrates
 
 
-def row_cost_from_prior(valid: torch.Tensor, prior: torch.Tensor) -> torch.Tensor:
-    """Estimated work per row from the validity mask and the DEPTHS prior plane ([rows, cols]); a pixel whose
-    prior is above -1 m is inverted from 1 m (samodel.c:963-967)."""
-    h = prior.abs().clamp(min=1.0).to(torch.float32)
+def row_cost_from_prior(valid: torch.Tensor, prior: torch.Tensor, prior_nodata: float | None = None) -> torch.Tensor:
+    """Estimated work per row from the validity mask and the DEPTHS prior plane ([rows, cols]), with the rules of the
+    C planner (photic_b200.cu:row_costs): a prior above -1 m is inverted from 1 m (samodel.c:963-967); a pixel whose
+    prior is nodata is inverted without one -- eight depth starts with all substrates (samodel.c:2222-2241)."""
+    h = torch.where(prior > -1.0, torch.ones_like(prior), prior.abs()).to(torch.float32)
     edges = torch.tensor(_COST_EDGES, dtype=torch.float32, device=prior.device)
     wts = torch.tensor(_COST_WEIGHT, dtype=torch.float32, device=prior.device)
     c = wts[torch.bucketize(h, edges, right=True)]
+    if prior_nodata is not None:
+        # approx_equal(prior, nodata, 1e-6), common.c:392 (float difference, products in double)
+        d = (prior - prior_nodata).abs().to(torch.float64)
+        big = torch.maximum(prior.abs().to(torch.float64), torch.full_like(d, abs(float(prior_nodata))))
+        c = torch.where(d <= big * 1.0e-6, torch.full_like(c, _COST_NO_PRIOR), c)
     return (c * valid.to(torch.float32)).sum(dim=1)
 
 

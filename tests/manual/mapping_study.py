@@ -18,6 +18,7 @@ from photic_b200.samodel import Inverter
 ap = argparse.ArgumentParser()
 ap.add_argument("--reps", type=int, default=4000)
 ap.add_argument("--ncu-list", action="store_true")
+ap.add_argument("--skews", default="0,900", help="start-time skew between the teams of an SM, cycles (0: all in step)")
 args = ap.parse_args()
 k = np.load(os.path.join(ROOT, "tests", "golden", "kat_objective.npz"))
 inv = Inverter(0)
@@ -30,14 +31,18 @@ if args.ncu_list:
 for tag, what in cases:
     ns, nb, nr, origin = (int(v) for v in k[f"{tag}_meta"])
     desc = capi.desc_from_spec(replace(scene.CONFIGS["murion"], n_dates=ns))
-    base = None
-    for tw, same in maps:
-        if not args.ncu_list:
-            inv.eval_bench(desc, nb, nr, origin, k[f"{tag}_meas"], k[f"{tag}_params"][0], tw, same, reps=50)  # warm-up
-        first, rate, ms = inv.eval_bench(desc, nb, nr, origin, k[f"{tag}_meas"], k[f"{tag}_params"][0], tw, same, reps=args.reps)
-        ok = np.float64(first).view(np.int64) == np.float64(k[f"{tag}_out"][0, 0]).view(np.int64)
-        if tw == 1:
-            base = rate
-        print(json.dumps({"case": what, "warps_per_pixel": tw, "team_on_one_scheduler": same, "pixels_in_flight_per_sm": 16 // tw,
-                          "evals_per_s": rate, "vs_warp_per_pixel": rate / base if base else None, "ms": ms, "reps": args.reps,
-                          "first_value_equals_reference": bool(ok)}), flush=True)
+    for skew in [int(v) for v in args.skews.split(",")]:
+        base = None
+        for tw, same in maps:
+            # one evaluation takes ~14 k cycles: `skew` cycles per team spread the teams of an SM over an evaluation
+            sk = skew * tw
+            if not args.ncu_list:
+                inv.eval_bench(desc, nb, nr, origin, k[f"{tag}_meas"], k[f"{tag}_params"][0], tw, same, reps=50)  # warm-up
+            first, rate, ms = inv.eval_bench(desc, nb, nr, origin, k[f"{tag}_meas"], k[f"{tag}_params"][0], tw, same, reps=args.reps,
+                                             skew_cycles=sk)
+            ok = np.float64(first).view(np.int64) == np.float64(k[f"{tag}_out"][0, 0]).view(np.int64)
+            if tw == 1:
+                base = rate
+            print(json.dumps({"case": what, "warps_per_pixel": tw, "team_on_one_scheduler": same, "pixels_in_flight_per_sm": 16 // tw,
+                              "skew_cycles_between_teams": sk, "evals_per_s": rate, "vs_warp_per_pixel": rate / base if base else None,
+                              "ms": ms, "reps": args.reps, "first_value_equals_reference": bool(ok)}), flush=True)
