@@ -395,23 +395,29 @@ static int launch_solve(phb_ctx *c, const ModelConst &M, SolveParams &sp, bool t
   cudaFuncAttributes fa0;
   CK(cudaFuncGetAttributes(&fa0, kern));
   const int W_reg = fa0.maxThreadsPerBlock / 32;
-  const int W_smem = (int)(((long long)c->smem_optin - sp.L.cta_bytes) / sp.L.warp_bytes);
+  /* CTAs per SM (experiment knob PHB_CTAS_PER_SM, default 1): k CTAs of 16 / k warps share the SM's shared memory (1 KB
+   * of it is reserved per CTA), registers and tensor memory */
+  int cps = 1;
+  if (const char *e = getenv("PHB_CTAS_PER_SM")) { int v = atoi(e); if (v == 2 || v == 4) cps = v; }
+  const long long smem_cta = ((long long)c->smem_optin + 1024) / cps - 1024;
+  const int W_smem = (int)((smem_cta - sp.L.cta_bytes) / sp.L.warp_bytes);
   if (W_smem < 1) return PHB_EINVAL; /* configuration does not fit shared memory */
   /* Occupancy vs simplex residency: each warp's leftover shared memory holds the first rows of its
    * simplex (all of it for sand-only pixels); the rest lives in an L2-resident global slab. Default:
    * 16 warps (4 per scheduler) when they fit; PHB_WARPS_PER_CTA overrides (tuning / profiling). */
-  int W = 16;
+  int W = 16 / cps;
   if (const char *e = getenv("PHB_WARPS_PER_CTA")) { int v = atoi(e); if (v >= 1) W = v; }
   if (W > W_reg) W = W_reg;
   if (W > W_smem) W = W_smem;
   if (W < 1) W = 1;
-  long long cache_bytes = ((long long)c->smem_optin - sp.L.cta_bytes) / W - sp.L.warp_bytes;
+  long long cache_bytes = (smem_cta - sp.L.cta_bytes) / W - sp.L.warp_bytes;
   if (cache_bytes > simplex_doubles * 8) cache_bytes = simplex_doubles * 8;
   if (const char *e = getenv("PHB_SIMPLEX_SMEM_BYTES")) { long long v = atoll(e); if (v >= 0 && v < cache_bytes) cache_bytes = v; }
   add_simplex_cache(sp.L, (int)cache_bytes);
   /* tensor memory (512 columns x 128 lanes per SM, idle on this path) holds the first simplex rows:
-   * warps sharing a lane quarter split the columns */
-  sp.L.tmem_cols = (512 / ((W + 3) / 4)) & ~1;
+   * warps sharing a lane quarter split the CTA's columns */
+  sp.tmem_alloc_cols = 512 / cps;
+  sp.L.tmem_cols = (sp.tmem_alloc_cols / ((W + 3) / 4)) & ~1;
   if (const char *e = getenv("PHB_TMEM")) { if (atoi(e) == 0) sp.L.tmem_cols = 0; }
   if (sp.n_classes > 1) {
     /* the sand-only class: same CTA-shared block and the same warp stride, a smaller fixed part (n = Nr + 2 Nr + 3 Ns
@@ -428,7 +434,7 @@ static int launch_solve(phb_ctx *c, const ModelConst &M, SolveParams &sp, bool t
   } else {
     sp.L1 = sp.L;
   }
-  int ctas = c->n_sm;
+  int ctas = c->n_sm * cps;
   if (const char *e = getenv("PHB_CTAS")) { int v = atoi(e); if (v >= 1) ctas = v; }
   const size_t smem = (size_t)sp.L.cta_bytes + (size_t)W * sp.L.warp_bytes;
   /* slab depth: the global-tier rows of the deepest simplex of either class (at least one row: nothing is ever empty) */

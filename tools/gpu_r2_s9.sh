@@ -17,5 +17,5 @@ if [ "$N" != "1" ]; then
   timeout 400 python tests/manual/rows_e2e.py --config exmouth --scene-planes 2>&1 | tail -1 | tee gpurun_out/r2s9_rows_e2e_n$N.json | tee -a $L
 fi
 echo "== pilbara + REFINE N=$N t=$((SECONDS-T0))s" | tee -a $L
-timeout 900 $TR tests/manual/run_scene.py --config pilbara --refine --check 24 2>&1 | tail -1 | tee -a $L
+timeout 900 $TR tests/manual/run_scene.py --config pilbara --refine --check ${PILBARA_CHECK:-24} 2>&1 | tail -1 | tee -a $L
 echo "done t=$((SECONDS-T0))s" | tee -a $L
