@@ -882,6 +882,16 @@ int host_band(phb_ctx *c, const phb_scene_desc *dd, int row_begin, int row_end, 
   return PHB_OK;
 }
 
+/* is [p, p + bytes) page-locked host memory (cudaHostAlloc / cudaHostRegister)? Then the copy engine can read or
+ * write it directly and the staging ring is skipped. */
+bool is_pinned(const void *p, size_t bytes) {
+  if (!p || bytes == 0) return false;
+  cudaPointerAttributes a0, a1;
+  if (cudaPointerGetAttributes(&a0, p) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+  if (cudaPointerGetAttributes(&a1, static_cast<const unsigned char *>(p) + bytes - 1) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+  return a0.type == cudaMemoryTypeHost && a1.type == cudaMemoryTypeHost;
+}
+
 /* rows [w0, w1) of the caller's rasters -> the band's device rasters */
 int band_upload(phb_shard *S, const RowSrc &src, long long w0, cudaStream_t st) {
   phb_ctx *c = S->ctx;
@@ -891,13 +901,21 @@ int band_upload(phb_shard *S, const RowSrc &src, long long w0, cudaStream_t st) 
   const size_t px = (size_t)nr * nc;
   int slot = 0;
   for (int g = 0; g < S->SB; g++) {
-    rc = ring_upload(c, slot, [&](long long r) { return src.row(g, r); }, w0, w0 + nr, nc,
-                     const_cast<float *>(S->view.planes) + g * px, st);
+    float *dst = const_cast<float *>(S->view.planes) + g * px;
+    if (src.planes && is_pinned(src.planes[g] + (size_t)w0 * nc, px * 4)) { /* contiguous and page-locked: one DMA */
+      CK(cudaMemcpyAsync(dst, src.planes[g] + (size_t)w0 * nc, px * 4, cudaMemcpyHostToDevice, st));
+      continue;
+    }
+    rc = ring_upload(c, slot, [&](long long r) { return src.row(g, r); }, w0, w0 + nr, nc, dst, st);
     if (rc) return rc;
   }
   if (S->view.prior) {
-    rc = ring_upload(c, slot, [&](long long r) { return src.prow(r); }, w0, w0 + nr, nc, const_cast<float *>(S->view.prior), st);
-    if (rc) return rc;
+    if (src.prior && is_pinned(src.prior + (size_t)w0 * nc, px * 4)) {
+      CK(cudaMemcpyAsync(const_cast<float *>(S->view.prior), src.prior + (size_t)w0 * nc, px * 4, cudaMemcpyHostToDevice, st));
+    } else {
+      rc = ring_upload(c, slot, [&](long long r) { return src.prow(r); }, w0, w0 + nr, nc, const_cast<float *>(S->view.prior), st);
+      if (rc) return rc;
+    }
   }
   return PHB_OK;
 }
@@ -912,8 +930,13 @@ int band_download(phb_shard *S, const RowDst &dst, const phb_outputs *flat_flags
   const float *dev9[9] = {d.depth, d.model_error, d.bottom_albedo, d.bottom_sand, d.bottom_seagrass, d.bottom_coral,
                           d.K_min, d.bottom_type, d.index_optical_depth};
   int rc;
+  const size_t own = (size_t)(r1 - r0) * nc;
   for (int k = 0; k < 9; k++) {
     if (!dst.scalar(k, r0)) continue;
+    if (dst.flat && is_pinned(dst.scalar(k, r0), own * 4)) { /* contiguous and page-locked: one DMA, no staging */
+      CK(cudaMemcpyAsync(dst.scalar(k, r0), dev9[k] + a, own * 4, cudaMemcpyDeviceToHost, st));
+      continue;
+    }
     rc = ring_download(c, [&](long long r) { return (void *)dst.scalar(k, r); }, r0, r1, nc, dev9[k] + a, 4, st);
     if (rc) return rc;
   }
@@ -929,13 +952,21 @@ int band_download(phb_shard *S, const RowDst &dst, const phb_outputs *flat_flags
   }
   if (flat_flags && flat_flags->converged) {
     uint8_t *h = flat_flags->converged;
-    rc = ring_download(c, [&](long long r) { return (void *)(h + (size_t)r * nc); }, r0, r1, nc, d.converged + a, 1, st);
-    if (rc) return rc;
+    if (is_pinned(h + (size_t)r0 * nc, own)) {
+      CK(cudaMemcpyAsync(h + (size_t)r0 * nc, d.converged + a, own, cudaMemcpyDeviceToHost, st));
+    } else {
+      rc = ring_download(c, [&](long long r) { return (void *)(h + (size_t)r * nc); }, r0, r1, nc, d.converged + a, 1, st);
+      if (rc) return rc;
+    }
   }
   if (flat_flags && flat_flags->n_evals) {
     int32_t *h = flat_flags->n_evals;
-    rc = ring_download(c, [&](long long r) { return (void *)(h + (size_t)r * nc); }, r0, r1, nc, d.n_evals + a, 4, st);
-    if (rc) return rc;
+    if (is_pinned(h + (size_t)r0 * nc, own * 4)) {
+      CK(cudaMemcpyAsync(h + (size_t)r0 * nc, d.n_evals + a, own * 4, cudaMemcpyDeviceToHost, st));
+    } else {
+      rc = ring_download(c, [&](long long r) { return (void *)(h + (size_t)r * nc); }, r0, r1, nc, d.n_evals + a, 4, st);
+      if (rc) return rc;
+    }
   }
   return PHB_OK;
 }

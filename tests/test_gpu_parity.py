@@ -243,6 +243,32 @@ def test_objective_extreme_parameters_take_the_fallback_paths(inverter, generic,
         assert eq.all(), (tag, np.argwhere(~eq)[:8], got[~eq][:8], k[f"{tag}_out"][~eq][:8])
 
 
+def test_pinned_host_buffers_equal_pageable_ones(inverter):
+    """Page-locked caller buffers are read and written by the copy engine directly, pageable ones go through the pinned
+    staging ring (photic_b200.cu: band_upload / band_download): same results either way, row window included."""
+    import torch
+    from photic_b200 import capi, scene
+    spec = scene.CONFIGS["exmouth"].scaled(41, 37)
+    planes, prior = scene.generate(spec)
+    desc = capi.desc_from_spec(spec)
+    want, st0 = inverter.invert_host(desc, planes.numpy(), prior.numpy(), scene_planes=False)
+    pp, pr = planes.clone().pin_memory(), prior.clone().pin_memory()
+    buf = {n: torch.zeros((spec.nrows, spec.ncols), dtype=torch.float32).pin_memory().numpy() for n in capi.SCALAR_PLANES}
+    buf["converged"] = torch.zeros((spec.nrows, spec.ncols), dtype=torch.uint8).pin_memory().numpy()
+    buf["n_evals"] = torch.zeros((spec.nrows, spec.ncols), dtype=torch.int32).pin_memory().numpy()
+    got, st1 = inverter.invert_host(desc, pp.numpy(), pr.numpy(), scene_planes=False, buffers=buf)
+    assert st1["n_valid"] == st0["n_valid"] > 300 and st1["n_evals"] == st0["n_evals"]
+    for name in list(capi.SCALAR_PLANES) + ["converged", "n_evals"]:
+        assert np.array_equal(got[name].view(np.uint8), want[name].view(np.uint8)), name
+    # a row window: only its rows are written
+    for name in buf:
+        buf[name][...] = 0
+    got, st2 = inverter.invert_host(desc, pp.numpy(), pr.numpy(), row_begin=9, row_end=30, scene_planes=False, buffers=buf)
+    for name in list(capi.SCALAR_PLANES) + ["converged", "n_evals"]:
+        assert np.array_equal(got[name][9:30].view(np.uint8), want[name][9:30].view(np.uint8)), name
+        assert not got[name][:9].any() and not got[name][30:].any(), name
+
+
 def test_team_objective_equals_warp_objective(inverter):
     """Mapping study (aux_kernels.cuh): the objective evaluated by a team of 2 / 4 / 8 warps -- terms dealt over the
     team's lanes, ordered sum and penalties on one warp -- gives the bits of the one-warp objective, which are the
