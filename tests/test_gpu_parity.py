@@ -57,6 +57,24 @@ def test_golden_scenes_bit_exact(inverter, name):
     assert (out["depth"][bad] == 0.0).all() and (out["K_min"][bad] == 0.0).all()
 
 
+@pytest.mark.parametrize("env", [{"PHB_WARPS_PER_CTA": "8"}, {"PHB_CTAS_PER_SM": "2"}, {"PHB_CTAS_PER_SM": "4", "PHB_ALIGN": "1"},
+                                 {"PHB_ALIGN": "1"}, {"PHB_TMEM": "0"}, {"PHB_SIMPLEX_SMEM_BYTES": "0"}])
+def test_launch_geometry_does_not_change_a_bit(inverter, env, monkeypatch):
+    """The tuning / profiling knobs of launch_solve (warps per CTA, CTAs per SM, aligned evaluations, tensor memory off,
+    no simplex rows in shared memory: every split of the simplex over its three storage tiers) only move work and data
+    around: records, evaluation counts and flags stay the reference's."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    for name in ("scene_exmouth", "scene_noprior"):
+        g = load_golden(name)
+        prior = g["prior"] if bool(g["use_prior"]) else None
+        out, st = inverter.invert_host(desc_from_golden(g), g["planes"], prior, debug=True)
+        ok = g["status"] == 1
+        assert st["n_valid"] == ok.sum()
+        assert np.array_equal(out["rec_evals"], g["n_evals"][ok]) and np.array_equal(out["rec_converged"], g["converged"][ok])
+        assert bits_equal(out["rec"], g["rec"][ok]).all(), (env, name)
+
+
 @pytest.mark.parametrize("name", MINED_FIXTURES)
 def test_mined_non_converged_and_restart_pixels_bit_exact(inverter, name):
     """Reference goldens of the rare pixels (tests/golden/make_golden.py make_mined / make_restarts): the device's
