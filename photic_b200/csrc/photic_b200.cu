@@ -361,22 +361,6 @@ int phb_debug_record_len(const phb_scene_desc *d) {
 
 struct LaunchGeom { int W, ctas, smem, regs; };
 
-/* the most simplex rows any pixel of a class leaves in the global slab (size_pixel() of invert_kernel.cuh, over every
- * neighbourhood size): the slabs are that deep, so all of them together are small enough to stay in L2 */
-static int max_global_rows(const SmemLayout &L, int NrMax, int Ns, int nb) {
-  int most = 0;
-  for (int Nr = 1; Nr <= NrMax; Nr++) {
-    const int n = Nr + 2 * Nr * nb + 3 * Ns, KB = (n + 31) >> 5;
-    int jT = (PHB_USE_TMEM && KB <= 3) ? L.tmem_cols / (2 * KB) : 0;
-    if (jT > n + 1) jT = n + 1;
-    int jS = L.simplex_doubles / n;
-    if (jT + jS > n + 1) jS = n + 1 - jT;
-    const int jG = n + 1 - jT - jS;
-    if (jG > most) most = jG;
-  }
-  return most;
-}
-
 /* Shared-memory layout, launch geometry and launch of the persistent solve kernel (pixel queues or, trials = true,
  * chains of depth-error trials). sp arrives with the work description filled in (views, classes, trial arrays); the
  * model, layouts, slabs, counters and libm tables are bound here. */
@@ -442,8 +426,7 @@ static int launch_solve(phb_ctx *c, const ModelConst &M, SolveParams &sp, bool t
   { const int r1 = max_global_rows(sp.L, NrMax, M.n_scenes, 1); if (r1 > slab_rows) slab_rows = r1; }
   if (sp.n_classes > 1) { const int r1 = max_global_rows(sp.L1, NrMax, M.n_scenes, 1); if (r1 > slab_rows) slab_rows = r1; }
   if (slab_rows < 1) slab_rows = 1;
-  const long long slab_doubles = (((long long)slab_rows * sp.L.nmax + sp.L.nmax + sp.L.Tmax +
-                                   (long long)((sp.L.nmax + 8) / 8 + 1) * sp.L.nmax /* centroid checkpoints */) + 15) & ~15LL;
+  const long long slab_doubles = slab_doubles_for(sp.L, slab_rows);
   CK(c->slabs.ensure((size_t)ctas * W * slab_doubles));
   sp.M = c->d_model;
   sp.slabs = c->slabs.p; sp.slab_stride = slab_doubles; sp.slab_rows = slab_rows;

@@ -217,6 +217,15 @@ const double kPowTab[3 * PHM_N] = PHM_POWLOG_TAB;
 
 void emu_warp_arrive() { yield_to_main(); }
 
+/* guard words behind the (exactly sized) slab: a write past the depth the host gives the slabs is caught here */
+static const int kSlabGuard = 64;
+static const double kGuardValue = -7.25e77;
+static bool slab_guard_intact(const std::vector<double> &slab, long long used) {
+  for (int g = 0; g < kSlabGuard; g++)
+    if (slab[used + g] != kGuardValue) return false;
+  return true;
+}
+
 extern "C" {
 
 int64_t emu_model_const_size(void) { return (int64_t)sizeof(phb::ModelConst); }
@@ -244,14 +253,20 @@ int emu_invert(const void *model, int64_t model_size, const float *planes, const
   memset(&sp, 0, sizeof(sp));
   sp.L = make_layout(M.SB, M.n_scenes, M.n_bottoms, NrMax);
   const long long simplex_doubles = (long long)(sp.L.nmax + 1) * sp.L.nmax;
-  const long long slab_doubles = simplex_doubles + sp.L.nmax + sp.L.Tmax + (long long)((sp.L.nmax + 8) / 8 + 1) * sp.L.nmax;
   long long cache = simplex_smem_bytes;
   if (cache > simplex_doubles * 8) cache = simplex_doubles * 8;
   add_simplex_cache(sp.L, (int)cache);
   sp.L.tmem_cols = 0;
+  /* the slab exactly as deep as the host library makes it (launch_solve), followed by guard words */
+  int slab_rows = max_global_rows(sp.L, NrMax, M.n_scenes, M.n_bottoms);
+  { const int r1 = max_global_rows(sp.L, NrMax, M.n_scenes, 1); if (r1 > slab_rows) slab_rows = r1; }
+  if (slab_rows < 1) slab_rows = 1;
+  const long long slab_doubles = slab_doubles_for(sp.L, slab_rows);
+  sp.slab_rows = slab_rows;
   if ((size_t)sp.L.cta_bytes + (size_t)sp.L.warp_bytes > sizeof(phb_smem)) return 2;
   memset(phb_smem, 0xcd, sizeof(phb_smem)); /* uninitialised shared memory is not zero on the device either */
-  std::vector<double> slab(slab_doubles, 0.0);
+  std::vector<double> slab(slab_doubles + kSlabGuard, 0.0);
+  for (int g = 0; g < kSlabGuard; g++) slab[slab_doubles + g] = kGuardValue;
   unsigned long long cnt[4] = {0, 0, 0, 0};
   double fl = 0.0;
   const size_t px = (size_t)M.nrows * M.ncols;
@@ -278,6 +293,7 @@ int emu_invert(const void *model, int64_t model_size, const float *planes, const
   run_warp();
   if (counters) memcpy(counters, cnt, sizeof(cnt));
   if (flops) *flops = fl;
+  if (!slab_guard_intact(slab, slab_doubles)) return 7; /* the kernel wrote past the slab depth */
   return 0;
 }
 
@@ -321,14 +337,20 @@ int emu_invert_raster(const void *model, int64_t model_size, const float *planes
   memset(&sp, 0, sizeof(sp));
   sp.L = make_layout(M.SB, M.n_scenes, M.n_bottoms, (2 * nsp - 1) * (2 * nsp - 1));
   const long long simplex_doubles = (long long)(sp.L.nmax + 1) * sp.L.nmax;
-  const long long slab_doubles = simplex_doubles + sp.L.nmax + sp.L.Tmax + (long long)((sp.L.nmax + 8) / 8 + 1) * sp.L.nmax;
   long long cache = simplex_smem_bytes;
   if (cache > simplex_doubles * 8) cache = simplex_doubles * 8;
   add_simplex_cache(sp.L, (int)cache);
   sp.L.tmem_cols = 0;
+  const int NrMax2 = (2 * nsp - 1) * (2 * nsp - 1);
+  int slab_rows = max_global_rows(sp.L, NrMax2, M.n_scenes, M.n_bottoms);
+  { const int r1 = max_global_rows(sp.L, NrMax2, M.n_scenes, 1); if (r1 > slab_rows) slab_rows = r1; }
+  if (slab_rows < 1) slab_rows = 1;
+  const long long slab_doubles = slab_doubles_for(sp.L, slab_rows);
+  sp.slab_rows = slab_rows;
   if ((size_t)sp.L.cta_bytes + (size_t)sp.L.warp_bytes > sizeof(phb_smem)) return 2;
   memset(phb_smem, 0xcd, sizeof(phb_smem));
-  std::vector<double> slab(slab_doubles, 0.0);
+  std::vector<double> slab(slab_doubles + kSlabGuard, 0.0);
+  for (int g = 0; g < kSlabGuard; g++) slab[slab_doubles + g] = kGuardValue;
   unsigned long long cnt[4] = {0, 0, 0, 0};
   double fl = 0.0;
   sp.M = &M;
@@ -353,6 +375,7 @@ int emu_invert_raster(const void *model, int64_t model_size, const float *planes
   g_params = &sp;
   g_body = body_solve;
   run_warp();
+  if (!slab_guard_intact(slab, slab_doubles)) return 7; /* the kernel wrote past the slab depth */
   return 0;
 }
 
