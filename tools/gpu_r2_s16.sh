@@ -1,0 +1,14 @@
+#!/bin/bash
+# round 2, session 16 (1 GPU): row-per-region term loop for 32 (scene,band) slots -- full GPU suite on the new library,
+# speed against the previous (validated) library on Exmouth- (6 dates, generic loop) and Qatar-shaped (8 dates) rasters
+mkdir -p gpurun_out
+T0=$SECONDS
+L=gpurun_out/r2s16.log
+echo "== gpu suite" | tee $L
+timeout 600 python -m pytest tests -q -m gpu 2>&1 | tail -4 | tee -a $L
+for lib in libphotic_b200.so libphotic_b200_prev.so; do
+  echo "== speed $lib: exmouth, qatar t=$((SECONDS-T0))s" | tee -a $L
+  PHB_LIB=$PWD/photic_b200/csrc/$lib timeout 100 python tools/profile_target.py 700 900 exmouth 2 2>&1 | tail -1 | tee -a $L
+  PHB_LIB=$PWD/photic_b200/csrc/$lib timeout 100 python tools/profile_target.py 700 900 qatar 2 2>&1 | tail -1 | tee -a $L
+done
+echo "done t=$((SECONDS-T0))s" | tee -a $L
