@@ -17,7 +17,7 @@ __global__ void kat_objective_kernel(const SolveParams p, int nb_active, int n_r
   __syncthreads();
   Warp w;
   const int lane = threadIdx.x & 31, SB = p.L.SB, Ns = p.L.Ns;
-  bind_warp(w, p, p.L, phb_smem, 0, 0);
+  bind_warp<0, 0>(w, p, p.L, phb_smem, 0, 0);
   Pixel px;
   px.Nr = n_regions; px.Nb = nb_active; px.origin = origin;
   size_pixel(px, lane, SB, Ns, p.L.simplex_doubles, 0);
@@ -214,7 +214,7 @@ eval_bench_kernel(const SolveParams p, int n_regions, int origin, const double *
   const int team = same_smsp ? warp % n_teams : warp / TW, wt = same_smsp ? warp / n_teams : warp % TW;
   const int bar_id = 1 + team, SB = p.L.SB, Ns = p.L.Ns;
   Warp w;
-  bind_warp(w, p, p.L, phb_smem, team, blockIdx.x * n_teams + team);
+  bind_warp<0, 0>(w, p, p.L, phb_smem, team, blockIdx.x * n_teams + team);
   Pixel px;
   px.Nr = n_regions; px.Nb = NB; px.origin = origin;
   size_pixel(px, lane, SB, Ns, p.L.simplex_doubles, 0);

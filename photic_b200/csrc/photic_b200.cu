@@ -375,6 +375,18 @@ static int launch_solve(phb_ctx *c, const ModelConst &M, SolveParams &sp, bool t
   void (*kern)(const SolveParams) = sp.L.SBP == 32 ? solve_kernel<0, 32, false> : solve_kernel<0, kMaxSB, false>;
   if (trials || !use_two_classes(M)) sp.n_classes = 1;
   if (sp.n_classes == 2) kern = sp.L.SBP == 32 ? solve_kernel<3, 32, false> : solve_kernel<3, kMaxSB, false>; /* the default NBOTTOMS */
+  /* the Landsat-8 configurations of BASELINE.json -- four bands per scene, 3 x 3 neighbourhoods, 4 / 6 / 8 dates -- have
+   * instantiations whose scene count and shared-memory layout are compile-time constants (PHB_CT_LAYOUT=0: off) */
+  {
+    bool four = true;
+    for (int s = 0; s < M.n_scenes; s++) four = four && M.n_bands[s] == 4;
+    const char *e = getenv("PHB_CT_LAYOUT");
+    if (sp.n_classes == 2 && sp.L.SBP == 32 && four && NrMax == 9 && !(e && atoi(e) == 0)) {
+      if (M.n_scenes == 4) kern = solve_kernel<3, 32, false, 4>;
+      else if (M.n_scenes == 6) kern = solve_kernel<3, 32, false, 6>;
+      else if (M.n_scenes == 8) kern = solve_kernel<3, 32, false, 8>;
+    }
+  }
   if (trials) kern = sp.L.SBP == 32 ? solve_kernel<0, 32, true> : solve_kernel<0, kMaxSB, true>;
   cudaFuncAttributes fa0;
   CK(cudaFuncGetAttributes(&fa0, kern));

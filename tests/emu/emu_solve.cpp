@@ -134,7 +134,7 @@ void kat_objective_body() {
   __syncthreads();
   Warp w;
   const int lane = threadIdx.x & 31, SB = p.L.SB, Ns = p.L.Ns;
-  bind_warp(w, p, p.L, phb_smem, 0, 0);
+  bind_warp<0, 0>(w, p, p.L, phb_smem, 0, 0);
   Pixel px;
   px.Nr = g_kat.n_regions; px.Nb = g_kat.nb_active; px.origin = g_kat.origin;
   size_pixel(px, lane, SB, Ns, p.L.simplex_doubles, 0);
@@ -217,6 +217,21 @@ const double kPowTab[3 * PHM_N] = PHM_POWLOG_TAB;
 
 void emu_warp_arrive() { yield_to_main(); }
 
+/* the instantiation launch_solve (csrc/photic_b200.cu) picks: compile-time layout for the Landsat-8 configurations */
+static void (*pick_solve_kernel(const phb::SolveParams &sp, const phb::ModelConst &M, bool two))(const phb::SolveParams) {
+  using namespace phb;
+  if (sp.L.SBP != 32) return two ? solve_kernel<3, kMaxSB, false> : solve_kernel<0, kMaxSB, false>;
+  bool four = true;
+  for (int s = 0; s < M.n_scenes; s++) four = four && M.n_bands[s] == 4;
+  const char *e = getenv("PHB_CT_LAYOUT");
+  if (two && four && sp.L.NrMax == 9 && !(e && atoi(e) == 0)) {
+    if (M.n_scenes == 4) return solve_kernel<3, 32, false, 4>;
+    if (M.n_scenes == 6) return solve_kernel<3, 32, false, 6>;
+    if (M.n_scenes == 8) return solve_kernel<3, 32, false, 8>;
+  }
+  return two ? solve_kernel<3, 32, false> : solve_kernel<0, 32, false>;
+}
+
 /* guard words behind the (exactly sized) slab: a write past the depth the host gives the slabs is caught here */
 static const int kSlabGuard = 64;
 static const double kGuardValue = -7.25e77;
@@ -286,8 +301,7 @@ int emu_invert(const void *model, int64_t model_size, const float *planes, const
   sp.dbg_rec = rec; sp.dbg_pix = pix; sp.dbg_iters = iters; sp.reclen = emu_record_len(model); sp.dbg_capacity = n_queue;
   sp.counters = cnt; sp.flops = &fl;
   sp.exp_tab = reinterpret_cast<const unsigned long long *>(kExpTab); sp.log_tab = kLogTab; sp.pow_tab = kPowTab;
-  if (sp.L.SBP == 32) g_kernel = band.two ? solve_kernel<3, 32, false> : solve_kernel<0, 32, false>;
-  else g_kernel = band.two ? solve_kernel<3, kMaxSB, false> : solve_kernel<0, kMaxSB, false>;
+  g_kernel = pick_solve_kernel(sp, M, band.two);
   g_params = &sp;
   g_body = body_solve;
   run_warp();
@@ -370,8 +384,7 @@ int emu_invert_raster(const void *model, int64_t model_size, const float *planes
   sp.dbg_rec = rec; sp.dbg_pix = pix; sp.dbg_iters = iters; sp.reclen = emu_record_len(model); sp.dbg_capacity = (long long)win;
   sp.counters = cnt; sp.flops = &fl;
   sp.exp_tab = reinterpret_cast<const unsigned long long *>(kExpTab); sp.log_tab = kLogTab; sp.pow_tab = kPowTab;
-  if (sp.L.SBP == 32) g_kernel = band.two ? solve_kernel<3, 32, false> : solve_kernel<0, 32, false>;
-  else g_kernel = band.two ? solve_kernel<3, kMaxSB, false> : solve_kernel<0, kMaxSB, false>;
+  g_kernel = pick_solve_kernel(sp, M, band.two);
   g_params = &sp;
   g_body = body_solve;
   run_warp();

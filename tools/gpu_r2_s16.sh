@@ -1,9 +1,9 @@
 #!/bin/bash
-# round 2, session 16 (1 GPU): row-per-region term loop for 32 (scene,band) slots -- full GPU suite on the new library,
-# speed against the previous (validated) library on Exmouth- (6 dates, generic loop) and Qatar-shaped (8 dates) rasters
+# round 2, sessions 16-17 (1 GPU): a kernel candidate (libphotic_b200.so) against the previous, validated library (_prev):
+# full GPU suite on the candidate, speed of both on Exmouth- (6 dates) and Qatar-shaped (8 dates) rasters
 mkdir -p gpurun_out
 T0=$SECONDS
-L=gpurun_out/r2s16.log
+L=gpurun_out/${1:-r2s16}.log
 echo "== gpu suite" | tee $L
 timeout 600 python -m pytest tests -q -m gpu 2>&1 | tail -4 | tee -a $L
 for lib in libphotic_b200.so libphotic_b200_prev.so; do
