@@ -371,11 +371,13 @@ def main():
             "e2e": e2e, "gpu_launches": 2 * K * world, "clocks": clocks,
         }
         # measured DRAM traffic of the kernel: bytes per pixel from the committed `ncu --set full` capture x pixels per launch
-        tpath = os.path.join(ROOT, "profiles", "r01_solve_kernel_traffic.json")
-        if os.path.exists(tpath):
-            tj = json.load(open(tpath))
-            line["roofline"]["traffic"] = tj["dram_bytes_per_pixel"] * total_px / (K * world)
-            line["roofline"]["traffic_source"] = "profiles/r01_solve_kernel_traffic.json (ncu dram__bytes_read+write per pixel) x pixels per launch"
+        for tname in ("r02_solve_kernel_traffic.json", "r01_solve_kernel_traffic.json"):
+            tpath = os.path.join(ROOT, "profiles", tname)
+            if os.path.exists(tpath):
+                tj = json.load(open(tpath))
+                line["roofline"]["traffic"] = tj["dram_bytes_per_pixel"] * total_px / (K * world)
+                line["roofline"]["traffic_source"] = f"profiles/{tname} (ncu dram__bytes_read+write per pixel) x pixels per launch"
+                break
         # algorithmic HBM traffic (reported, not binding): planes + prior in, 9 planes + flags out
         bytes_px = spec.n_planes * 4 + 4 + 9 * 4 + 5
         line["roofline"]["hbm_gbs_algorithmic"] = bytes_px * rb * spec.ncols * K / (total_ms * 1e-3) / 1e9
