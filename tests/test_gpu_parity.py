@@ -58,11 +58,12 @@ def test_golden_scenes_bit_exact(inverter, name):
 
 
 @pytest.mark.parametrize("env", [{"PHB_WARPS_PER_CTA": "8"}, {"PHB_CTAS_PER_SM": "2"}, {"PHB_CTAS_PER_SM": "4", "PHB_ALIGN": "1"},
-                                 {"PHB_ALIGN": "1"}, {"PHB_TMEM": "0"}, {"PHB_SIMPLEX_SMEM_BYTES": "0"}])
+                                 {"PHB_ALIGN": "1"}, {"PHB_TMEM": "0"}, {"PHB_SIMPLEX_SMEM_BYTES": "0"}, {"PHB_CT_LAYOUT": "0"}])
 def test_launch_geometry_does_not_change_a_bit(inverter, env, monkeypatch):
     """The tuning / profiling knobs of launch_solve (warps per CTA, CTAs per SM, aligned evaluations, tensor memory off,
-    no simplex rows in shared memory: every split of the simplex over its three storage tiers) only move work and data
-    around: records, evaluation counts and flags stay the reference's."""
+    no simplex rows in shared memory: every split of the simplex over its three storage tiers; the run-time-layout
+    instantiation instead of the compile-time one) only move work and data around: records, evaluation counts and flags
+    stay the reference's."""
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     for name in ("scene_exmouth", "scene_noprior"):
